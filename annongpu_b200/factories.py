@@ -1,0 +1,287 @@
+"""Synthetic-input factories for the VMC hot path (host side, numpy only).
+
+Seeded restatements of the reference's random-init factories — ``pyANNonGPU/new_RBM.py:14-29``,
+``pyANNonGPU/new_neural_network.py:31-131``, ``pyANNonGPU/new_convolutional_network.py:30-82`` — that
+return plain *specs* (dataclasses of numpy arrays).  A spec can be turned into a device object of this
+package (``spec.build()``), or handed to any other implementation of the same interface.
+
+The reference builds operators from ``QuantumExpression.PauliExpression`` (absent here); the raw
+form it reduces them to is (coefficient, a-mask, b-mask) per Pauli string
+(``source/operator/Operator.cpp:18-39``) with X=(1,0), Y=(0,1), Z=(1,1)
+(``include/basis/PauliString.hpp:37-56``).  ``PauliSum`` below is that raw form with arbitrary-width
+masks (Python ints), so N > 64 sites is representable.
+"""
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+
+def _real_noise(rng, shape):
+    return 2.0 * rng.random(shape) - 1.0
+
+
+def _complex_noise(rng, shape):
+    return _real_noise(rng, shape) + 1j * _real_noise(rng, shape)
+
+
+def _noise_vector(rng, shape, real):
+    return _real_noise(rng, shape) if real else _complex_noise(rng, shape)
+
+
+def words_for(num_sites):
+    return (int(num_sites) + 63) // 64
+
+
+def masks_to_words(masks, words):
+    """list of Python-int bitmasks -> uint64 array (len, words), little-endian words."""
+    out = np.zeros((len(masks), words), dtype=np.uint64)
+    for n, m in enumerate(masks):
+        m = int(m)
+        for w in range(words):
+            out[n, w] = (m >> (64 * w)) & 0xFFFFFFFFFFFFFFFF
+    return out
+
+
+# ---------------------------------------------------------------------------- operators
+
+@dataclass
+class PauliSum:
+    """Sum of Pauli strings in the reference's raw (coefficient, a, b) form."""
+    num_sites: int
+    coeffs: list = field(default_factory=list)
+    a: list = field(default_factory=list)
+    b: list = field(default_factory=list)
+
+    def add(self, coeff, paulis):
+        """paulis: dict site -> 'X' | 'Y' | 'Z'."""
+        a = b = 0
+        for site, kind in paulis.items():
+            assert 0 <= site < self.num_sites
+            if kind in ("X", "Z"):
+                a |= 1 << site
+            if kind in ("Y", "Z"):
+                b |= 1 << site
+        self.coeffs.append(complex(coeff))
+        self.a.append(a)
+        self.b.append(b)
+        return self
+
+    @property
+    def num_strings(self):
+        return len(self.coeffs)
+
+    @property
+    def words(self):
+        return words_for(self.num_sites)
+
+    def arrays(self, words=None):
+        words = words or self.words
+        return (np.asarray(self.coeffs, dtype=np.complex128), masks_to_words(self.a, words), masks_to_words(self.b, words))
+
+    def build(self, gpu=True):
+        from .api import Operator
+        return Operator(self, gpu)
+
+
+def ring_bonds(n):
+    return [(i, (i + 1) % n) for i in range(n)]
+
+
+def square_lattice_bonds(rows, cols):
+    """Periodic rows x cols lattice, site = row * cols + col; 2 * rows * cols bonds."""
+    bonds = []
+    for r in range(rows):
+        for c in range(cols):
+            s = r * cols + c
+            bonds.append((s, r * cols + (c + 1) % cols))
+            bonds.append((s, ((r + 1) % rows) * cols + c))
+    return bonds
+
+
+def tfim(num_sites, bonds, J=1.0, h=1.0):
+    """-J sum_<ij> Z_i Z_j - h sum_i X_i   (SURVEY.md §8d)."""
+    H = PauliSum(num_sites)
+    for i, j in bonds:
+        H.add(-J, {i: "Z", j: "Z"})
+    for i in range(num_sites):
+        H.add(-h, {i: "X"})
+    return H
+
+
+def heisenberg(num_sites, bonds, J=1.0):
+    """J sum_<ij> (X_i X_j + Y_i Y_j + Z_i Z_j)   (SURVEY.md §8d)."""
+    H = PauliSum(num_sites)
+    for i, j in bonds:
+        for k in "XYZ":
+            H.add(J, {i: k, j: k})
+    return H
+
+
+# ---------------------------------------------------------------------------- wavefunction specs
+
+@dataclass
+class RBMSpec:
+    W: np.ndarray
+    final_weight: complex
+    log_prefactor: complex = 0.0
+
+    @property
+    def num_sites(self):
+        return self.W.shape[0]
+
+    def build(self, gpu=True):
+        from .api import PsiRBM
+        return PsiRBM(self.W, self.final_weight, self.log_prefactor, gpu)
+
+
+@dataclass
+class DeepSpec:
+    num_sites: int
+    input_weights: np.ndarray
+    biases: list
+    connections: list
+    weights: list
+    final_weights: np.ndarray
+    log_prefactor: complex = 0.0
+
+    def build(self, gpu=True):
+        from .api import PsiDeep
+        return PsiDeep(self.num_sites, self.input_weights, self.biases, self.connections, self.weights,
+                       self.final_weights, self.log_prefactor, gpu)
+
+
+@dataclass
+class CNNSpec:
+    extent: tuple
+    num_channels_list: np.ndarray
+    connectivity_list: np.ndarray
+    symmetry_classes: np.ndarray
+    params: np.ndarray
+    final_factor: float
+    log_prefactor: complex = 0.0
+
+    @property
+    def num_sites(self):
+        return int(np.prod(self.extent))
+
+    def build(self, gpu=True):
+        from .api import PsiCNN
+        return PsiCNN(self.extent, self.num_channels_list, self.connectivity_list, self.symmetry_classes,
+                      self.params, self.final_factor, self.log_prefactor, gpu)
+
+
+def rbm_spec(N, M, initial_value=(0.01 + 1j * math.pi / 4), noise=1e-4, final_weight=10, seed=0):
+    """pyANNonGPU/new_RBM.py:14-29 with an explicit seed."""
+    assert M >= N
+    rng = np.random.default_rng(seed)
+    W = noise * _complex_noise(rng, (N, M))
+    for alpha in range(M // N):
+        W[:, alpha * N:(alpha + 1) * N] += initial_value * np.eye(N)
+    return RBMSpec(W, complex(final_weight), 0.0)
+
+
+def _prod(xs):
+    r = 1
+    for x in xs:
+        r *= x
+    return r
+
+
+def deep_spec(num_sites, N, M, C, initial_value=(0.01 + 1j * math.pi / 4), a=0, noise=1e-4,
+              noise_modulation="auto", final_weights=10, seed=0):
+    """pyANNonGPU/new_neural_network.py:31-131 (1-D connectivity form) with an explicit seed."""
+    assert not isinstance(N, (list, tuple)), "only the 1-D form is restated here"
+    rng = np.random.default_rng(seed)
+    for n, m, c in zip([N] + M[:-1], M, C):
+        assert (m * c) % n == 0 and c <= n
+    a = a * np.ones(N, dtype=complex) if isinstance(a, (float, int, complex)) else np.array(a, dtype=complex)
+    is_real = (complex(initial_value).imag == 0)
+
+    b = [noise * _noise_vector(rng, m, is_real).astype(complex) for m in M]
+    w = (noise * _noise_vector(rng, (C[0], M[0]), is_real)).astype(complex)
+    w[C[0] // 2, :] += initial_value
+    W = [w]
+    if noise_modulation == "auto":
+        noise_modulation = [math.sqrt(6 / (c + next_c)) for c, m, next_c in zip(C[1:], M[1:], C[2:] + [1])]
+    for c, m, next_c, nm in zip(C[1:], M[1:], C[2:] + [1], noise_modulation):
+        W.append((math.sqrt(6 / (c + next_c)) * _real_noise(rng, (c, m)) + noise * _noise_vector(rng, (c, m), is_real)).astype(complex))
+
+    def delta_func(n, m, c):
+        if m > n:
+            return 1
+        if n % m == 0:
+            return n // m
+        return c
+
+    connections = []
+    for n, m, c in zip([N] + M[:-1], M, C):
+        dj = delta_func(n, m, c)
+        connections.append(np.array([[(j * dj + i) % n for j in range(m)] for i in range(c)], dtype=np.uint32))
+
+    if isinstance(final_weights, (float, int)):
+        final_weights = final_weights * np.ones(M[-1])
+    assert len(final_weights) == M[-1]
+    return DeepSpec(num_sites, a, b, connections, W, np.asarray(final_weights, dtype=complex), 0.0)
+
+
+def cnn_spec(L, layers, initial_value=(0.01 + 1j * math.pi / 4), noise=1e-4, final_factor=10,
+             symmetry_classes=None, real=False, seed=0):
+    """pyANNonGPU/new_convolutional_network.py:30-82 with an explicit seed. L is padded to 3 dims (leading 1s),
+    matching the bound type PsiCNN_t<3> (include/quantum_state/PsiCNN.hpp:381)."""
+    rng = np.random.default_rng(seed)
+    L = list(L)
+    layers = [(nc, list(conn)) for nc, conn in layers]
+    while len(L) < 3:
+        L = [1] + L
+        layers = [(nc, [1] + conn) for nc, conn in layers]
+    num_channels_list = np.array([nc for nc, _ in layers], dtype=np.uint32)
+    connectivity_list = np.array([conn for _, conn in layers], dtype=np.uint32)
+    if symmetry_classes is None:
+        symmetry_classes = np.zeros(_prod(L), dtype=np.uint32)
+    num_symmetry_classes = len(set(int(s) for s in symmetry_classes))
+
+    params = []
+    for layer, (num_channels, nd_conn) in enumerate(layers):
+        for c, l in zip(nd_conn, L):
+            assert c <= l
+        connectivity = _prod(nd_conn)
+        num_prev = layers[layer - 1][0] if layer > 0 else 1
+        for _ in range(num_channels * num_prev):
+            for _ in range(num_symmetry_classes):
+                link = (noise * _noise_vector(rng, connectivity, real)).astype(complex)
+                if layer == 0:
+                    link[connectivity // 2] = complex(initial_value).real if real else initial_value
+                else:
+                    link += math.sqrt(6 / (connectivity * num_prev + connectivity * num_channels)) * _real_noise(rng, connectivity)
+                params += list(link)
+    return CNNSpec(tuple(L), num_channels_list, connectivity_list, np.asarray(symmetry_classes, dtype=np.uint32),
+                   np.array(params, dtype=complex), float(final_factor), 0.0)
+
+
+# ---------------------------------------------------------------------------- BASELINE.json configurations
+
+def config_C1():
+    """PsiRBM alpha=2, N=16, TFIM ring, ExactSummation."""
+    return rbm_spec(16, 32, noise=1e-2, final_weight=10, seed=1234), tfim(16, ring_bonds(16))
+
+
+def config_C2(N=64, alpha=4):
+    """PsiRBM alpha=4, N=64, Heisenberg ring, 8192 chains."""
+    return rbm_spec(N, alpha * N, noise=0.02 / math.sqrt(alpha), final_weight=1, seed=1234), heisenberg(N, ring_bonds(N))
+
+
+def config_C3():
+    """PsiCNN 10x10, 3 layers x 3 channels, 3x3 kernels, J1 Heisenberg, 32768 chains."""
+    return cnn_spec([10, 10], [(3, [3, 3])] * 3, noise=1e-2, final_factor=1, seed=1236), heisenberg(100, square_lattice_bonds(10, 10))
+
+
+def config_C4():
+    """PsiDeep 64 -> 64 -> 64 on the 8x8 TFIM."""
+    return (deep_spec(64, 64, [64, 64], [64, 64], noise=1e-3, a=0, final_weights=1, seed=1235),
+            tfim(64, square_lattice_bonds(8, 8)))
+
+
+def config_C5(N=200, alpha=8):
+    """PsiRBM alpha=8, N=200, Heisenberg ring, 131072 chains over 8 GPUs."""
+    return rbm_spec(N, alpha * N, noise=0.02 / math.sqrt(alpha), final_weight=1, seed=1234), heisenberg(N, ring_bonds(N))
