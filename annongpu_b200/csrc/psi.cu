@@ -1,0 +1,400 @@
+// Host-side wavefunction objects: parameter bookkeeping + kernel launches.
+#include "psi.hpp"
+#include "rbm_kernels.cuh"
+#include <algorithm>
+#include <set>
+
+namespace angpu {
+
+static Ctx g_ctx;
+Ctx& ctx() { return g_ctx; }
+
+void ctx_init(int device) {
+    if(g_ctx.device == device && g_ctx.stream) return;
+    ANGPU_CUDA(cudaSetDevice(device));
+    if(g_ctx.own_stream && g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
+    ANGPU_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+    g_ctx.own_stream = true;
+    g_ctx.device = device;
+    cudaDeviceProp prop;
+    ANGPU_CUDA(cudaGetDeviceProperties(&prop, device));
+    g_ctx.num_sms = prop.multiProcessorCount;
+    g_ctx.smem_optin = prop.sharedMemPerBlockOptin;
+}
+
+// ---------------------------------------------------------------------------------------- generic launches
+
+namespace {
+
+struct WarpCfg { unsigned wpb, grid; size_t smem; };
+
+// one warp per item; warps per block limited by the per-warp scratch slice
+WarpCfg warp_cfg(unsigned pl_elems, size_t items) {
+    const size_t slice = warp_slice_bytes(pl_elems);
+    const size_t budget = std::min<size_t>(ctx().smem_optin, 200 * 1024);
+    ANGPU_REQUIRE(slice <= budget, "model scratch does not fit in shared memory");
+    unsigned wpb = (unsigned)std::min<size_t>(8, budget / slice);
+    // keep >= 2 blocks per SM resident when the slice allows it
+    while(wpb > 1 && wpb * slice > budget / 2) wpb--;
+    const size_t blocks_needed = (items + wpb - 1) / wpb;
+    const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>(blocks_needed, (size_t)ctx().num_sms * 16));
+    return WarpCfg{wpb, grid, wpb * slice};
+}
+
+template<class F>
+void set_smem(F* kernel, size_t smem) {
+    if(smem > 48 * 1024) ANGPU_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+}
+
+template<class Dev>
+void generic_log_psi(const Dev& d, SampleSet& S, bool es_weights) {
+    if(S.ns == 0) return;
+    const WarpCfg c = warp_cfg(d.payload_elems(), S.ns);
+    set_smem(k_log_psi<Dev>, c.smem);
+    k_log_psi<Dev><<<c.grid, c.wpb * 32, c.smem, stream()>>>(d, S.conf.p, S.ns, S.log_psi.p, es_weights ? S.weight.p : nullptr);
+    ANGPU_CHECK_LAUNCH(); count_launch();
+}
+template<class Dev>
+void generic_eloc(const Dev& d, const Operator& op, SampleSet& S) {
+    if(S.ns == 0) return;
+    ANGPU_REQUIRE(op.words == d.words, "operator / wavefunction word count mismatch");
+    const WarpCfg c = warp_cfg(d.payload_elems(), S.ns);
+    set_smem(k_eloc<Dev>, c.smem);
+    k_eloc<Dev><<<c.grid, c.wpb * 32, c.smem, stream()>>>(d, op.dev, S.conf.p, S.log_psi.p, S.ns, S.eloc.p);
+    ANGPU_CHECK_LAUNCH(); count_launch();
+}
+template<class Dev>
+void generic_ok(const Dev& d, SampleSet& S, size_t s0, size_t cnt, cplx* out) {
+    if(cnt == 0) return;
+    const WarpCfg c = warp_cfg(d.payload_elems(), cnt);
+    set_smem(k_ok<Dev>, c.smem);
+    k_ok<Dev><<<c.grid, c.wpb * 32, c.smem, stream()>>>(d, S.conf.p + s0 * d.words, cnt, out);
+    ANGPU_CHECK_LAUNCH(); count_launch();
+}
+template<class Dev>
+void generic_mc(const Dev& d, const McParams& mc, SampleSet& S, unsigned long long* acc_rej_dev) {
+    if(mc.num_chains_local == 0) return;
+    const size_t slice = warp_slice_bytes(d.payload_elems());
+    const size_t budget = std::min<size_t>(ctx().smem_optin, 200 * 1024);
+    ANGPU_REQUIRE(slice <= budget, "model scratch does not fit in shared memory");
+    unsigned wpb = (unsigned)std::min<size_t>(4, budget / slice);
+    while(wpb > 1 && wpb * slice > budget / 2) wpb--;
+    const unsigned grid = ceil_div(mc.num_chains_local, wpb);
+    set_smem(k_mc<Dev>, wpb * slice);
+    k_mc<Dev><<<grid, wpb * 32, wpb * slice, stream()>>>(d, mc, S.conf.p, S.log_psi.p, acc_rej_dev);
+    ANGPU_CHECK_LAUNCH(); count_launch();
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------- PsiRBM
+
+PsiRBM::PsiRBM(unsigned N_, unsigned M_, const cplx* W, cplx fw_, cplx lp_) {
+    kind = RBM; N = N_; M = M_; words = words_for(N); P = N * M; lp = lp_; fw = fw_;
+    ANGPU_REQUIRE(N >= 1 && N <= 64u * MAXW, "PsiRBM: 1 <= N <= 256");
+    ANGPU_REQUIRE(M >= 1, "PsiRBM: M >= 1");
+    hW.assign(W, W + (size_t)N * M);
+    upload();
+}
+void PsiRBM::upload() {
+    dW.upload(hW);
+    std::vector<cplx> t((size_t)N * M);
+    for(unsigned i = 0; i < N; i++) for(unsigned j = 0; j < M; j++) t[(size_t)j * N + i] = hW[(size_t)i * M + j];
+    dWt.upload(t);
+}
+void PsiRBM::log_psi(SampleSet& S, bool es_weights) {
+    if(S.ns == 0) return;
+    S.angles.resize(S.ns * M);
+    const unsigned wpb = 8, grid = (unsigned)std::min<size_t>((S.ns + wpb - 1) / wpb, (size_t)ctx().num_sms * 16);
+    k_rbm_angles<<<grid, wpb * 32, 0, stream()>>>(dev(), S.conf.p, S.ns, S.angles.p, S.log_psi.p, es_weights ? S.weight.p : nullptr);
+    ANGPU_CHECK_LAUNCH(); count_launch();
+    S.has_angles = true;
+}
+void PsiRBM::ensure_angles(SampleSet& S) {
+    if(S.has_angles || S.ns == 0) return;
+    S.angles.resize(S.ns * M);
+    const unsigned wpb = 8, grid = (unsigned)std::min<size_t>((S.ns + wpb - 1) / wpb, (size_t)ctx().num_sms * 16);
+    k_rbm_angles<<<grid, wpb * 32, 0, stream()>>>(dev(), S.conf.p, S.ns, S.angles.p, nullptr, nullptr);
+    ANGPU_CHECK_LAUNCH(); count_launch();
+    S.has_angles = true;
+}
+void PsiRBM::eloc(const Operator& op, SampleSet& S) {
+    if(S.ns == 0) return;
+    ANGPU_REQUIRE(op.words == words, "operator / wavefunction word count mismatch");
+    const size_t slice = rbm_eloc_slice_bytes(M, op.dev.num_groups);
+    const size_t budget = std::min<size_t>(ctx().smem_optin, 200 * 1024);
+    if(op.dev.max_flips > (unsigned)RBM_ELOC_MAXF || slice > budget) { generic_eloc(dev(), op, S); return; }
+    ensure_angles(S);
+    unsigned wpb = (unsigned)std::min<size_t>(8, budget / slice);
+    while(wpb > 1 && wpb * slice > budget / 2) wpb--;
+    const unsigned grid = (unsigned)std::min<size_t>((S.ns + wpb - 1) / wpb, (size_t)ctx().num_sms * 16);
+    set_smem(k_eloc_rbm, wpb * slice);
+    k_eloc_rbm<<<grid, wpb * 32, wpb * slice, stream()>>>(dev(), op.dev, S.conf.p, S.angles.p, S.ns, S.eloc.p);
+    ANGPU_CHECK_LAUNCH(); count_launch();
+}
+void PsiRBM::compute_T(SampleSet& S, DevBuf<cplx>& T) {
+    ensure_angles(S);
+    T.resize(S.ns * M);
+    if(S.ns == 0) return;
+    const size_t total = S.ns * M;
+    const unsigned grid = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)ctx().num_sms * 32);
+    k_rbm_T<<<grid, 256, 0, stream()>>>(dev(), S.angles.p, total, T.p);
+    ANGPU_CHECK_LAUNCH(); count_launch();
+}
+void PsiRBM::ok_rows(SampleSet& S, size_t s0, size_t cnt, cplx* out) {
+    if(cnt == 0) return;
+    DevBuf<cplx> T;
+    compute_T(S, T);
+    k_rbm_dense_O<<<(unsigned)cnt, 256, 0, stream()>>>(dev(), S.conf.p + s0 * words, T.p + s0 * M, cnt, out);
+    ANGPU_CHECK_LAUNCH(); count_launch();
+    ANGPU_CUDA(cudaStreamSynchronize(stream()));   // T is freed on return
+}
+
+template<int K>
+static void launch_mc_rbm(const RbmDev& d, const McParams& mc, SampleSet& S, unsigned long long* acc_rej_dev) {
+    const unsigned wpb = 4, grid = ceil_div(mc.num_chains_local, wpb);
+    if(d.fw.im == 0.0)
+        k_mc_rbm<K, true><<<grid, wpb * 32, 0, stream()>>>(d, mc, S.conf.p, S.log_psi.p, S.angles.p, acc_rej_dev);
+    else
+        k_mc_rbm<K, false><<<grid, wpb * 32, 0, stream()>>>(d, mc, S.conf.p, S.log_psi.p, S.angles.p, acc_rej_dev);
+    ANGPU_CHECK_LAUNCH(); count_launch();
+}
+void PsiRBM::mc_sample(const McParams& mc, SampleSet& S, unsigned long long* acc_rej_dev) {
+    if(mc.num_chains_local == 0) return;
+    const RbmDev d = dev();
+    if(M <= 512u) {
+        S.angles.resize(S.ns * M);
+        if(M <= 32u) launch_mc_rbm<1>(d, mc, S, acc_rej_dev);
+        else if(M <= 64u) launch_mc_rbm<2>(d, mc, S, acc_rej_dev);
+        else if(M <= 128u) launch_mc_rbm<4>(d, mc, S, acc_rej_dev);
+        else if(M <= 256u) launch_mc_rbm<8>(d, mc, S, acc_rej_dev);
+        else launch_mc_rbm<16>(d, mc, S, acc_rej_dev);
+        S.has_angles = true;
+    } else {
+        generic_mc(d, mc, S, acc_rej_dev);
+        S.has_angles = false;
+    }
+}
+
+// ---------------------------------------------------------------------------------------- PsiDeep
+
+PsiDeep::PsiDeep(unsigned num_sites_, unsigned N_, const cplx* input_weights_, unsigned num_hidden, const unsigned* sizes,
+                 const unsigned* conn, const cplx* biases, const unsigned* lhs_connections, const cplx* lhs_weights,
+                 const cplx* final_weights_, cplx lp_) {
+    kind = DEEP; num_sites = num_sites_; N = N_; words = words_for(num_sites_); lp = lp_;
+    ANGPU_REQUIRE(N == num_sites, "PsiDeep: only the spin basis (N == num_sites) is on the hot path");
+    ANGPU_REQUIRE(N >= 1 && N <= 64u * MAXW, "PsiDeep: 1 <= N <= 256");
+    ANGPU_REQUIRE(num_hidden >= 1 && num_hidden + 1 <= (unsigned)DEEP_MAX_LAYERS, "PsiDeep: 1..4 hidden layers");
+    num_layers = num_hidden + 1;
+    input_weights.assign(input_weights_, input_weights_ + N);
+    layers.resize(num_layers);
+    layers[0].size = N; width = N; P = N;
+    size_t off_b = 0, off_w = 0; unsigned deep = 0;
+    for(unsigned l = 1; l < num_layers; l++) {
+        Layer& L = layers[l];
+        L.size = sizes[l - 1]; L.conn = conn[l - 1];
+        ANGPU_REQUIRE((size_t)L.size * L.conn % layers[l - 1].size == 0, "PsiDeep: size*conn must be a multiple of the previous layer size");
+        width = std::max(width, L.size);
+        const size_t nw = (size_t)L.size * L.conn;
+        L.bias.assign(biases + off_b, biases + off_b + L.size);
+        L.lhs_w.assign(lhs_weights + off_w, lhs_weights + off_w + nw);
+        L.lhs_c.assign(lhs_connections + off_w, lhs_connections + off_w + nw);
+        for(unsigned c : L.lhs_c) ANGPU_REQUIRE(c < layers[l - 1].size, "PsiDeep: connection index out of range");
+        L.begin_params = P; P += L.size + (unsigned)nw;
+        if(l > 1) { L.begin_deep = deep; deep += L.size; }
+        off_b += L.size; off_w += nw;
+    }
+    num_deep = deep;
+    final_weights.assign(final_weights_, final_weights_ + layers[num_layers - 1].size);
+    compile_rhs();
+    upload();
+}
+PsiDeep::PsiDeep(const PsiDeep& o) {
+    kind = DEEP; N = o.N; words = o.words; P = o.P; lp = o.lp;
+    num_sites = o.num_sites; num_layers = o.num_layers; width = o.width; num_deep = o.num_deep;
+    input_weights = o.input_weights; final_weights = o.final_weights;
+    layers.resize(num_layers);
+    for(unsigned l = 0; l < num_layers; l++) {
+        Layer& a = layers[l]; const Layer& b = o.layers[l];
+        a.size = b.size; a.conn = b.conn; a.rhs_conn = b.rhs_conn; a.begin_params = b.begin_params; a.begin_deep = b.begin_deep;
+        a.lhs_c = b.lhs_c; a.rhs_c = b.rhs_c; a.lhs_w = b.lhs_w; a.rhs_w = b.rhs_w; a.bias = b.bias;
+    }
+    upload();
+}
+// source/quantum_state/PsiDeep.cu:214-242
+void PsiDeep::compile_rhs() {
+    for(unsigned l = 0; l + 1 < num_layers; l++) {
+        Layer& lo = layers[l]; const Layer& hi = layers[l + 1];
+        lo.rhs_conn = hi.size * hi.conn / lo.size;
+        lo.rhs_c.assign((size_t)lo.size * lo.rhs_conn, 0u);
+        lo.rhs_w.assign((size_t)lo.size * lo.rhs_conn, cplx(0.0, 0.0));
+        std::vector<unsigned> fill(lo.size, 0u);
+        for(unsigned j = 0; j < hi.size; j++)
+            for(unsigned i = 0; i < hi.conn; i++) {
+                const unsigned lhs = hi.lhs_c[(size_t)i * hi.size + j];
+                ANGPU_REQUIRE(fill[lhs] < lo.rhs_conn, "PsiDeep: connectivity is not regular (each unit must feed rhs_connectivity units)");
+                lo.rhs_c[(size_t)lhs * lo.rhs_conn + fill[lhs]] = j;
+                lo.rhs_w[(size_t)lhs * lo.rhs_conn + fill[lhs]] = hi.lhs_w[(size_t)i * hi.size + j];
+                fill[lhs]++;
+            }
+    }
+    layers[num_layers - 1].rhs_conn = 0;
+}
+void PsiDeep::upload() {
+    for(auto& L : layers) {
+        L.d_lhs_c.upload(L.lhs_c); L.d_rhs_c.upload(L.rhs_c);
+        L.d_lhs_w.upload(L.lhs_w); L.d_rhs_w.upload(L.rhs_w); L.d_bias.upload(L.bias);
+    }
+    d_final.upload(final_weights);
+}
+DeepDev PsiDeep::dev() const {
+    DeepDev d{};
+    d.N = N; d.words = words; d.P = P; d.num_layers = num_layers; d.width = width; d.num_deep = num_deep; d.lp = lp;
+    for(unsigned l = 0; l < num_layers; l++) {
+        const Layer& L = layers[l];
+        d.L[l] = DeepLayerDev{L.size, L.conn, L.rhs_conn, L.begin_params, L.begin_deep,
+                              L.d_lhs_c.p, L.d_rhs_c.p, L.d_lhs_w.p, L.d_rhs_w.p, L.d_bias.p};
+    }
+    d.final_w = d_final.p;
+    return d;
+}
+// source/quantum_state/PsiDeep.cu:246-270
+void PsiDeep::get_params(cplx* out) const {
+    std::memcpy(out, input_weights.data(), sizeof(cplx) * N); out += N;
+    for(unsigned l = 1; l < num_layers; l++) {
+        const Layer& L = layers[l];
+        std::memcpy(out, L.bias.data(), sizeof(cplx) * L.size); out += L.size;
+        std::memcpy(out, L.lhs_w.data(), sizeof(cplx) * L.lhs_w.size()); out += L.lhs_w.size();
+    }
+}
+// source/quantum_state/PsiDeep.cu:274-305
+void PsiDeep::set_params(const cplx* in) {
+    input_weights.assign(in, in + N); in += N;
+    for(unsigned l = 1; l < num_layers; l++) {
+        Layer& L = layers[l];
+        L.bias.assign(in, in + L.size); in += L.size;
+        const size_t nw = L.lhs_w.size();
+        L.lhs_w.assign(in, in + nw); in += nw;
+    }
+    compile_rhs();
+    upload();
+}
+void PsiDeep::log_psi(SampleSet& S, bool es_weights) { generic_log_psi(dev(), S, es_weights); }
+void PsiDeep::eloc(const Operator& op, SampleSet& S) { generic_eloc(dev(), op, S); }
+void PsiDeep::ok_rows(SampleSet& S, size_t s0, size_t cnt, cplx* out) { generic_ok(dev(), S, s0, cnt, out); }
+void PsiDeep::mc_sample(const McParams& mc, SampleSet& S, unsigned long long* a) { generic_mc(dev(), mc, S, a); }
+
+// ---------------------------------------------------------------------------------------- PsiCNN
+
+PsiCNN::PsiCNN(const unsigned* extent_, unsigned num_layers_, const unsigned* num_channels_, const unsigned* connectivity_,
+               const unsigned* symmetry_classes, const cplx* params_, unsigned num_params, double final_factor_, cplx lp_) {
+    kind = CNN; lp = lp_; final_factor = final_factor_; num_layers = num_layers_;
+    for(int d = 0; d < 3; d++) extent[d] = extent_[d];
+    N = extent[0] * extent[1] * extent[2]; words = words_for(N); P = num_params;
+    ANGPU_REQUIRE(N >= 1 && N <= 64u * MAXW, "PsiCNN: 1 <= N <= 256");
+    ANGPU_REQUIRE(num_layers >= 1 && num_layers <= (unsigned)CNN_MAX_LAYERS, "PsiCNN: 1..4 layers");
+    num_channels.assign(num_channels_, num_channels_ + num_layers);
+    connectivity.assign(connectivity_, connectivity_ + 3 * num_layers);
+    sym.assign(symmetry_classes, symmetry_classes + N);
+    params.assign(params_, params_ + P);
+    build();
+}
+// source/quantum_state/PsiCNN.cpp:10-55 (parameter layout), detail/Convolve.hpp:108-141 (neighbours)
+void PsiCNN::build() {
+    // distinct symmetry-class labels must be 0..num_sym-1 for the weight layout sym*vol + c to be dense
+    std::set<unsigned> classes(sym.begin(), sym.end());
+    num_sym = (unsigned)classes.size();
+    for(unsigned s : sym) ANGPU_REQUIRE(s < num_sym, "PsiCNN: symmetry classes must be labelled 0..num_classes-1");
+    unsigned off = 0; num_angles = 0; maxch = 1;
+    h_nbr.assign(num_layers, {}); h_inv.assign(num_layers, {});
+    d_nbr.clear(); d_inv.clear(); d_nbr.resize(num_layers); d_inv.resize(num_layers);
+    const unsigned page = extent[1] * extent[2];
+    for(unsigned l = 0; l < num_layers; l++) {
+        CnnLayerDev& L = layer_dev[l];
+        L.nch = num_channels[l]; L.prev = l > 0 ? num_channels[l - 1] : 1u;
+        ANGPU_REQUIRE(L.nch * L.prev <= (unsigned)CNN_MAX_LINKS, "PsiCNN: too many channel links in a layer");
+        maxch = std::max(maxch, L.nch);
+        const unsigned* c = &connectivity[3 * l];
+        L.vol = c[0] * c[1] * c[2];
+        L.begin_params = off;
+        for(unsigned ci = 0; ci < L.prev; ci++) for(unsigned cj = 0; cj < L.nch; cj++) { L.link_begin[ci * L.nch + cj] = off; off += num_sym * L.vol; }
+        L.num_params = off - L.begin_params;
+        L.angle_off = num_angles; num_angles += L.nch * N;
+        h_nbr[l].resize((size_t)N * L.vol); h_inv[l].resize((size_t)N * L.vol);
+        for(unsigned x = 0; x < N; x++) {
+            const unsigned pg = x / page, row = (x % page) / extent[2], col = (x % page) % extent[2];
+            unsigned cidx = 0;
+            for(unsigned k = 0; k < c[0]; k++) for(unsigned i = 0; i < c[1]; i++) for(unsigned j = 0; j < c[2]; j++, cidx++) {
+                const unsigned y = ((pg + k) % extent[0]) * page + ((row + i) % extent[1]) * extent[2] + ((col + j) % extent[2]);
+                h_nbr[l][(size_t)x * L.vol + cidx] = y;
+            }
+        }
+        // inverse: for every (y, c) the unique x with nbr(x, c) == y
+        for(unsigned x = 0; x < N; x++) for(unsigned cidx = 0; cidx < L.vol; cidx++) h_inv[l][(size_t)h_nbr[l][(size_t)x * L.vol + cidx] * L.vol + cidx] = x;
+        d_nbr[l].upload(h_nbr[l]); d_inv[l].upload(h_inv[l]);
+        L.nbr = d_nbr[l].p; L.inv = d_inv[l].p;
+    }
+    ANGPU_REQUIRE(off == P, "PsiCNN: parameter count does not match the layer description");
+    d_sym.upload(sym); d_params.upload(params);
+}
+CnnDev PsiCNN::dev() const {
+    CnnDev d{};
+    d.N = N; d.words = words; d.P = P; d.num_layers = num_layers; d.num_sym = num_sym; d.num_angles = num_angles; d.maxch = maxch;
+    d.final_factor = final_factor; d.lp = lp; d.sym = d_sym.p; d.params = d_params.p;
+    for(unsigned l = 0; l < num_layers; l++) d.L[l] = layer_dev[l];
+    return d;
+}
+void PsiCNN::log_psi(SampleSet& S, bool es_weights) { generic_log_psi(dev(), S, es_weights); }
+void PsiCNN::eloc(const Operator& op, SampleSet& S) { generic_eloc(dev(), op, S); }
+void PsiCNN::ok_rows(SampleSet& S, size_t s0, size_t cnt, cplx* out) { generic_ok(dev(), S, s0, cnt, out); }
+void PsiCNN::mc_sample(const McParams& mc, SampleSet& S, unsigned long long* a) { generic_mc(dev(), mc, S, a); }
+
+// ---------------------------------------------------------------------------------------- PsiClassical
+
+PsiClassical::PsiClassical(unsigned num_sites, unsigned order_, unsigned num_ops_, const Operator* const* ops_, const cplx* params_,
+                           unsigned num_own, const PsiCNN* ref_, cplx lp_) {
+    kind = CLASSICAL; N = num_sites; words = words_for(N); order = order_; num_ops = num_ops_; lp = lp_;
+    ANGPU_REQUIRE(order == 1u || order == 2u, "PsiClassical: order must be 1 or 2");
+    ANGPU_REQUIRE(num_own == num_ops, "PsiClassical: one parameter per local operator");
+    for(unsigned i = 0; i < num_ops; i++) {
+        ANGPU_REQUIRE(ops_[i]->words == words, "PsiClassical: operator word count mismatch");
+        ops.emplace_back(new Operator(*ops_[i]));
+    }
+    own_params.assign(params_, params_ + num_own);
+    if(ref_) ref.reset(static_cast<PsiCNN*>(ref_->clone()));
+    P = num_own + ((order > 1u && ref) ? ref->P : 0u);
+    upload();
+}
+void PsiClassical::upload() {
+    std::vector<OpDev> v;
+    for(auto& o : ops) v.push_back(o->dev);
+    d_ops.upload(v); d_params.upload(own_params);
+}
+ClassicalDev PsiClassical::dev() const {
+    ClassicalDev d{};
+    d.N = N; d.words = words; d.P = P; d.num_ops = num_ops; d.order = order; d.lp = lp;
+    d.ops = d_ops.p; d.params = d_params.p; d.has_ref = (bool)ref;
+    if(ref) d.ref = ref->dev();
+    return d;
+}
+Psi* PsiClassical::clone() const {
+    std::vector<const Operator*> o;
+    for(auto& p : ops) o.push_back(p.get());
+    return new PsiClassical(N, order, num_ops, o.data(), own_params.data(), (unsigned)own_params.size(), ref.get(), lp);
+}
+// source/quantum_state/PsiClassical.cu:36-70
+void PsiClassical::get_params(cplx* out) const {
+    std::memcpy(out, own_params.data(), sizeof(cplx) * own_params.size());
+    if(order > 1u && ref) ref->get_params(out + own_params.size());
+}
+void PsiClassical::set_params(const cplx* in) {
+    own_params.assign(in, in + own_params.size());
+    d_params.upload(own_params);
+    if(order > 1u && ref) ref->set_params(in + own_params.size());
+}
+void PsiClassical::log_psi(SampleSet& S, bool es_weights) { generic_log_psi(dev(), S, es_weights); }
+void PsiClassical::eloc(const Operator& op, SampleSet& S) { generic_eloc(dev(), op, S); }
+void PsiClassical::ok_rows(SampleSet& S, size_t s0, size_t cnt, cplx* out) { generic_ok(dev(), S, s0, cnt, out); }
+void PsiClassical::mc_sample(const McParams& mc, SampleSet& S, unsigned long long* a) { generic_mc(dev(), mc, S, a); }
+
+} // namespace angpu

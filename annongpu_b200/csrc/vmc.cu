@@ -1,0 +1,740 @@
+// Ensembles, reductions over samples, ExpectationValue / TDVP, S.v, CG and dense solve.
+#include "vmc.hpp"
+#include <cusolverDn.h>
+#include <algorithm>
+#include <cmath>
+
+namespace angpu {
+
+static allreduce_fn g_allreduce = nullptr;
+static void* g_allreduce_user = nullptr;
+void set_allreduce(allreduce_fn fn, void* user) { g_allreduce = fn; g_allreduce_user = user; }
+void allreduce_sum(double* dev_ptr, size_t count) {
+    if(g_allreduce && count) g_allreduce(dev_ptr, (unsigned long long)count, g_allreduce_user);
+}
+
+// ============================================================================================ small kernels
+
+__global__ void k_fill(double* p, double v, size_t n) {
+    for(size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+// Spins::enumerate (include/basis/Spins.h:65-77, 291-296): basis index == bitmask in word 0
+__global__ void k_enumerate(uint64_t* conf, size_t begin, size_t n, unsigned words) {
+    for(size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        conf[i * words] = (uint64_t)(begin + i);
+        for(unsigned w = 1; w < words; w++) conf[i * words + w] = 0ull;
+    }
+}
+
+constexpr int RED_T = 1024;
+// deterministic block reduction of NV doubles per thread (fixed tree order)
+template<int NV>
+__device__ void block_reduce(double (&v)[NV], double* out) {
+    __shared__ double sm[NV][RED_T / 32];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    #pragma unroll
+    for(int i = 0; i < NV; i++) { v[i] = warp_sum(v[i]); if(lane == 0) sm[i][warp] = v[i]; }
+    __syncthreads();
+    if(warp == 0) {
+        #pragma unroll
+        for(int i = 0; i < NV; i++) {
+            double x = (lane < blockDim.x / 32) ? sm[i][lane] : 0.0;
+            x = warp_sum(x);
+            if(lane == 0) out[i] = x;
+        }
+    }
+    __syncthreads();
+}
+
+// out4 = {Re sum w E, Im sum w E, sum w |E|^2, sum w};  lp2 (optional) = sum w log psi
+__global__ void __launch_bounds__(RED_T) k_scalar_sums(const double* __restrict__ w, const cplx* __restrict__ eloc,
+                                                       const cplx* __restrict__ log_psi, size_t ns, double* out4, double* lp2) {
+    double v[6] = {0, 0, 0, 0, 0, 0};
+    for(size_t s = threadIdx.x; s < ns; s += RED_T) {
+        const double ws = w[s];
+        if(eloc) { const cplx e = eloc[s]; v[0] += ws * e.re; v[1] += ws * e.im; v[2] += ws * abs2(e); }
+        v[3] += ws;
+        if(log_psi) { const cplx l = log_psi[s]; v[4] += ws * l.re; v[5] += ws * l.im; }
+    }
+    double r[6];
+    block_reduce<6>(v, r);
+    if(threadIdx.x == 0) {
+        if(out4) { out4[0] = r[0]; out4[1] = r[1]; out4[2] = r[2]; out4[3] = r[3]; }
+        if(lp2) { lp2[0] = r[4]; lp2[1] = r[5]; }
+    }
+}
+
+// out = sum_k op(a_k) b_k, op = conj if CONJ_A  (single block, deterministic)
+template<bool CONJ_A>
+__global__ void __launch_bounds__(RED_T) k_dot(const cplx* __restrict__ a, const cplx* __restrict__ b, size_t n, cplx* out) {
+    double v[2] = {0, 0};
+    for(size_t k = threadIdx.x; k < n; k += RED_T) {
+        cplx x = a[k]; if(CONJ_A) x = conj(x);
+        const cplx p = x * b[k];
+        v[0] += p.re; v[1] += p.im;
+    }
+    double r[2];
+    block_reduce<2>(v, r);
+    if(threadIdx.x == 0) *out = cplx(r[0], r[1]);
+}
+
+// ============================================================================================ column reductions
+// mean_k = sum_s w_s O_sk ;  x_k = sum_s w_s X_s conj(O_sk)   over the samples of one chunk (blockIdx.y)
+
+__global__ void __launch_bounds__(128) k_col_reduce_dense(const cplx* __restrict__ O, const double* __restrict__ w,
+        const cplx* __restrict__ X, size_t ns, unsigned P, size_t chunk, cplx* __restrict__ part_mean, cplx* __restrict__ part_x) {
+    const unsigned k = blockIdx.x * 128u + threadIdx.x;
+    const size_t s0 = (size_t)blockIdx.y * chunk, s1 = min(ns, s0 + chunk);
+    if(k >= P) return;
+    cplx m(0.0, 0.0), x(0.0, 0.0);
+    for(size_t s = s0; s < s1; s++) {
+        const cplx o = O[s * P + k];
+        const double ws = w[s];
+        m.re = fma(ws, o.re, m.re); m.im = fma(ws, o.im, m.im);
+        const cplx wx = ws * X[s];
+        cfma(x, wx, conj(o));
+    }
+    if(part_mean) part_mean[(size_t)blockIdx.y * P + k] = m;
+    part_x[(size_t)blockIdx.y * P + k] = x;
+}
+
+// PsiRBM factorised rows O_s,(i,j) = sigma_si T_sj: thread = column j, 8 sites per thread
+constexpr int RBM_IT = 8;
+__global__ void __launch_bounds__(128) k_col_reduce_rbm(const uint64_t* __restrict__ conf, const cplx* __restrict__ T,
+        const double* __restrict__ w, const cplx* __restrict__ X, size_t ns, unsigned N, unsigned M, unsigned words, size_t chunk,
+        cplx* __restrict__ part_mean, cplx* __restrict__ part_x) {
+    const unsigned j = blockIdx.x * 128u + threadIdx.x;
+    const unsigned i0 = blockIdx.y * RBM_IT;
+    const size_t s0 = (size_t)blockIdx.z * chunk, s1 = min(ns, s0 + chunk);
+    if(j >= M) return;
+    cplx m[RBM_IT], x[RBM_IT];
+    #pragma unroll
+    for(int ii = 0; ii < RBM_IT; ii++) { m[ii] = cplx(0.0, 0.0); x[ii] = cplx(0.0, 0.0); }
+    const unsigned word = i0 >> 6, shift = i0 & 63u;     // RBM_IT divides 64: the 8 sites share one word
+    for(size_t s = s0; s < s1; s++) {
+        const cplx t = T[s * M + j];
+        const double ws = w[s];
+        const cplx a = ws * t, b = (ws * X[s]) * conj(t);
+        const unsigned bits = (unsigned)(conf[s * words + word] >> shift);
+        #pragma unroll
+        for(int ii = 0; ii < RBM_IT; ii++) {
+            const double sg = ((bits >> ii) & 1u) ? 1.0 : -1.0;
+            m[ii].re = fma(sg, a.re, m[ii].re); m[ii].im = fma(sg, a.im, m[ii].im);
+            x[ii].re = fma(sg, b.re, x[ii].re); x[ii].im = fma(sg, b.im, x[ii].im);
+        }
+    }
+    const size_t P = (size_t)N * M;
+    #pragma unroll
+    for(int ii = 0; ii < RBM_IT; ii++) {
+        const unsigned i = i0 + ii;
+        if(i < N) {
+            if(part_mean) part_mean[(size_t)blockIdx.z * P + (size_t)i * M + j] = m[ii];
+            part_x[(size_t)blockIdx.z * P + (size_t)i * M + j] = x[ii];
+        }
+    }
+}
+
+// out[k] = sum_ch part[ch][k]  (fixed order)
+__global__ void k_sum_chunks(const cplx* __restrict__ part, unsigned chunks, size_t P, cplx* __restrict__ out) {
+    for(size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < P; k += (size_t)gridDim.x * blockDim.x) {
+        cplx a(0.0, 0.0);
+        for(unsigned c = 0; c < chunks; c++) a += part[(size_t)c * P + k];
+        out[k] = a;
+    }
+}
+
+// a_s = O_s . v   (dense rows; one block per sample)
+__global__ void __launch_bounds__(256) k_rowdot_dense(const cplx* __restrict__ O, const cplx* __restrict__ v, unsigned P, cplx* __restrict__ a) {
+    const size_t s = blockIdx.x;
+    cplx acc(0.0, 0.0);
+    for(unsigned k = threadIdx.x; k < P; k += 256u) cfma(acc, O[s * P + k], v[k]);
+    __shared__ cplx sm[8];
+    acc = warp_sum(acc);
+    if((threadIdx.x & 31u) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if(threadIdx.x == 0) { cplx r(0.0, 0.0); for(int i = 0; i < 8; i++) r += sm[i]; a[s] = r; }
+}
+
+// a_s = sum_j T_sj (sum_i sigma_si v_ij)   (PsiRBM factorised rows; block = 8 samples, threads over j)
+constexpr int RBM_ST = 8;
+__global__ void __launch_bounds__(256) k_rowdot_rbm(const uint64_t* __restrict__ conf, const cplx* __restrict__ T, const cplx* __restrict__ v,
+        size_t ns, unsigned N, unsigned M, unsigned words, cplx* __restrict__ a) {
+    const size_t sb = (size_t)blockIdx.x * RBM_ST;
+    __shared__ uint64_t sconf[RBM_ST][MAXW];
+    __shared__ cplx sm[RBM_ST][8];
+    if(threadIdx.x < RBM_ST * MAXW) {
+        const unsigned st = threadIdx.x / MAXW, wd = threadIdx.x % MAXW;
+        sconf[st][wd] = (sb + st < ns && wd < words) ? conf[(sb + st) * words + wd] : 0ull;
+    }
+    __syncthreads();
+    cplx tot[RBM_ST];
+    #pragma unroll
+    for(int st = 0; st < RBM_ST; st++) tot[st] = cplx(0.0, 0.0);
+    for(unsigned j = threadIdx.x; j < M; j += 256u) {
+        cplx inner[RBM_ST];
+        #pragma unroll
+        for(int st = 0; st < RBM_ST; st++) inner[st] = cplx(0.0, 0.0);
+        for(unsigned i = 0; i < N; i++) {
+            const cplx x = v[(size_t)i * M + j];
+            #pragma unroll
+            for(int st = 0; st < RBM_ST; st++) {
+                const double sg = ((sconf[st][i >> 6] >> (i & 63u)) & 1ull) ? 1.0 : -1.0;
+                inner[st].re = fma(sg, x.re, inner[st].re); inner[st].im = fma(sg, x.im, inner[st].im);
+            }
+        }
+        #pragma unroll
+        for(int st = 0; st < RBM_ST; st++) if(sb + st < ns) cfma(tot[st], T[(sb + st) * M + j], inner[st]);
+    }
+    #pragma unroll
+    for(int st = 0; st < RBM_ST; st++) {
+        const cplx r = warp_sum(tot[st]);
+        if((threadIdx.x & 31u) == 0) sm[st][threadIdx.x >> 5] = r;
+    }
+    __syncthreads();
+    if(threadIdx.x < RBM_ST && sb + threadIdx.x < ns) {
+        cplx r(0.0, 0.0);
+        for(int i = 0; i < 8; i++) r += sm[threadIdx.x][i];
+        a[sb + threadIdx.x] = r;
+    }
+}
+
+// F_k = F'_k - E conj(Obar_k)      (TDVP.cu.template:300, 331-333)
+__global__ void k_finalize_F(const cplx* __restrict__ packed, unsigned P, cplx* __restrict__ F) {
+    const cplx E = packed[0];
+    for(size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < P; k += (size_t)gridDim.x * blockDim.x)
+        F[k] = packed[2 + P + k] - E * conj(packed[2 + k]);
+}
+// out_k -= conj(Obar_k) * dot      (TDVP.cu.template:435-442)
+__global__ void k_sv_correct(const cplx* __restrict__ Obar, const cplx* __restrict__ dot, unsigned P, cplx* __restrict__ out) {
+    const cplx d = *dot;
+    for(size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < P; k += (size_t)gridDim.x * blockDim.x)
+        out[k] -= conj(Obar[k]) * d;
+}
+
+// ============================================================================================ S matrix
+// S'[r][c] = sum_s w_s conj(O_sr) O_sc  — Hermitian rank-k update, upper-triangular 64x64 tiles, split over samples.
+constexpr int ZT = 64, ZK = 8;
+__global__ void __launch_bounds__(256) k_zherk(const cplx* __restrict__ O, const double* __restrict__ w, size_t ns, unsigned P,
+                                               size_t chunk, cplx* __restrict__ Sout, size_t split_stride) {
+    // decode the upper-triangular tile index
+    const unsigned nt = (P + ZT - 1) / ZT;
+    unsigned t = blockIdx.x, tr = 0;
+    while(t >= nt - tr) { t -= nt - tr; tr++; }
+    const unsigned tc = tr + t;
+    const size_t s0 = (size_t)blockIdx.y * chunk, s1 = min(ns, s0 + chunk);
+    __shared__ cplx A[ZK][ZT], B[ZK][ZT];
+    const unsigned tx = threadIdx.x & 15u, ty = threadIdx.x >> 4;
+    cplx acc[4][4];
+    #pragma unroll
+    for(int i = 0; i < 4; i++)
+        #pragma unroll
+        for(int j = 0; j < 4; j++) acc[i][j] = cplx(0.0, 0.0);
+    for(size_t sb = s0; sb < s1; sb += ZK) {
+        // 256 threads load 2 x (ZK x ZT) elements
+        for(unsigned e = threadIdx.x; e < ZK * ZT; e += 256u) {
+            const unsigned kk = e / ZT, col = e % ZT;
+            const size_t s = sb + kk;
+            cplx a(0.0, 0.0), b(0.0, 0.0);
+            if(s < s1) {
+                const unsigned r = tr * ZT + col, c = tc * ZT + col;
+                if(r < P) a = w[s] * conj(O[s * P + r]);
+                if(c < P) b = O[s * P + c];
+            }
+            A[kk][col] = a; B[kk][col] = b;
+        }
+        __syncthreads();
+        #pragma unroll
+        for(int kk = 0; kk < ZK; kk++) {
+            cplx a[4], b[4];
+            #pragma unroll
+            for(int i = 0; i < 4; i++) { a[i] = A[kk][ty + 16 * i]; b[i] = B[kk][tx + 16 * i]; }
+            #pragma unroll
+            for(int i = 0; i < 4; i++)
+                #pragma unroll
+                for(int j = 0; j < 4; j++) cfma(acc[i][j], a[i], b[j]);
+        }
+        __syncthreads();
+    }
+    cplx* Sp = Sout + (size_t)blockIdx.y * split_stride;
+    #pragma unroll
+    for(int i = 0; i < 4; i++)
+        #pragma unroll
+        for(int j = 0; j < 4; j++) {
+            const unsigned r = tr * ZT + ty + 16 * i, c = tc * ZT + tx + 16 * j;
+            if(r < P && c < P) {
+                Sp[(size_t)r * P + c] = acc[i][j];
+                if(tr != tc) Sp[(size_t)c * P + r] = conj(acc[i][j]);
+            }
+        }
+}
+// S = sum_splits S' - conj(Obar_r) Obar_c     (TDVP.cu.template:293-299);  also adds nothing else
+__global__ void k_S_finalize(const cplx* __restrict__ Spart, unsigned splits, size_t split_stride, const cplx* __restrict__ Obar,
+                             unsigned P, cplx* __restrict__ S, bool subtract_mean) {
+    const size_t total = (size_t)P * P;
+    for(size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        cplx a(0.0, 0.0);
+        for(unsigned c = 0; c < splits; c++) a += Spart[(size_t)c * split_stride + e];
+        if(subtract_mean) { const size_t r = e / P, c = e % P; a -= conj(Obar[r]) * Obar[c]; }
+        S[e] = a;
+    }
+}
+
+// ============================================================================================ solver kernels
+// scal layout (cplx): [0] rs_old, [1] pAp, [2] rs_new, [3] scratch
+__global__ void k_cg_xr(cplx* x, cplx* r, const cplx* p, const cplx* Ap, const cplx* scal, size_t n) {
+    const double alpha = scal[0].re / scal[1].re;
+    for(size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+        x[k] += alpha * p[k];
+        r[k] -= alpha * Ap[k];
+    }
+}
+__global__ void k_cg_p(cplx* p, const cplx* r, cplx* scal, size_t n) {
+    const double beta = scal[2].re / scal[0].re;
+    for(size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
+        p[k] = r[k] + beta * p[k];
+}
+__global__ void k_cg_roll(cplx* scal) { scal[0] = scal[2]; }
+__global__ void k_add_shift(cplx* Ap, const cplx* p, const double* diag, double shift_abs, double shift_rel, size_t n) {
+    for(size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
+        Ap[k] += (shift_abs + shift_rel * diag[k]) * p[k];
+}
+__global__ void k_scale_vec(const cplx* in, cplx phase, cplx* out, size_t n, bool conj_in) {
+    for(size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+        cplx v = in[k]; if(conj_in) v = conj(v);
+        out[k] = phase * v;
+    }
+}
+__global__ void k_conj_inplace(cplx* v, size_t n) {
+    for(size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) v[k] = conj(v[k]);
+}
+// diag_k = sum_s w_s |O_sk|^2 - |Obar_k|^2
+__global__ void k_diag_dense(const cplx* __restrict__ O, const double* __restrict__ w, size_t ns, unsigned P, double* __restrict__ d) {
+    const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+    if(k >= P) return;
+    double a = 0.0;
+    for(size_t s = 0; s < ns; s++) a = fma(w[s], abs2(O[s * P + k]), a);
+    d[k] = a;
+}
+__global__ void k_diag_rbm(const cplx* __restrict__ T, const double* __restrict__ w, size_t ns, unsigned N, unsigned M, double* __restrict__ d) {
+    const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+    if(j >= M) return;
+    double a = 0.0;
+    for(size_t s = 0; s < ns; s++) a = fma(w[s], abs2(T[s * M + j]), a);
+    for(unsigned i = 0; i < N; i++) d[(size_t)i * M + j] = a;
+}
+__global__ void k_diag_finalize(double* d, const cplx* Obar, size_t n) {
+    for(size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) d[k] -= abs2(Obar[k]);
+}
+__global__ void k_add_diag_shift(cplx* A, const double* diag, double shift_abs, double shift_rel, unsigned P) {
+    for(size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < P; k += (size_t)gridDim.x * blockDim.x)
+        A[k * (size_t)P + k].re += shift_abs + shift_rel * diag[k];
+}
+__global__ void k_exp_inplace(cplx* v, size_t n) {
+    for(size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) v[k] = cexp(v[k]);
+}
+__global__ void k_mul_exp(const cplx* log_psi, const cplx* eloc, cplx* out, size_t n) {
+    for(size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) out[k] = cexp(log_psi[k]) * eloc[k];
+}
+__global__ void k_sum_rows(const cplx* __restrict__ O, size_t ns, unsigned P, cplx* __restrict__ out) {
+    const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+    if(k >= P) return;
+    cplx a(0.0, 0.0);
+    for(size_t s = 0; s < ns; s++) a += O[s * P + k];
+    out[k] = a;
+}
+
+static inline unsigned grid_for(size_t n, unsigned block = 256) {
+    return (unsigned)std::max<size_t>(1, std::min<size_t>((n + block - 1) / block, (size_t)ctx().num_sms * 32));
+}
+
+// ============================================================================================ Ensemble
+
+void Ensemble::generate(Psi& psi, SampleSet& S) {
+    if(is_mc) {
+        ANGPU_REQUIRE(num_chains >= 1 && num_samples >= 1, "MonteCarlo: num_samples and num_markov_chains must be positive");
+        size_t c0, cn; shard(num_chains, c0, cn);
+        McParams mc{};
+        mc.num_samples = num_samples; mc.num_sweeps = num_sweeps; mc.num_therm = num_therm;
+        mc.steps_per_chain = (unsigned)(num_samples / num_chains);
+        mc.num_chains_local = (unsigned)cn; mc.chain0 = (unsigned)c0;
+        mc.seed_lo = (unsigned)seed; mc.seed_hi = (unsigned)(seed >> 32); mc.call = call;
+        S.resize((size_t)mc.steps_per_chain * cn, psi.words);
+        d_acc_rej.resize(2); d_acc_rej.zero();
+        psi.mc_sample(mc, S, d_acc_rej.p);
+        if(S.ns) { k_fill<<<grid_for(S.ns), 256, 0, stream()>>>(S.weight.p, 1.0 / (double)num_samples, S.ns); ANGPU_CHECK_LAUNCH(); count_launch(); }
+        call++;
+    } else {
+        ANGPU_REQUIRE(num_sites == psi.N, "ExactSummation: num_sites differs from the wavefunction's");
+        ANGPU_REQUIRE(num_sites <= 40u, "ExactSummation: too many sites");
+        size_t b, n; shard((size_t)1 << num_sites, b, n);
+        S.resize(n, psi.words);
+        if(n) { k_enumerate<<<grid_for(n), 256, 0, stream()>>>(S.conf.p, b, n, psi.words); ANGPU_CHECK_LAUNCH(); count_launch(); }
+        psi.log_psi(S, true);
+    }
+}
+void Ensemble::acceptance(unsigned long long out[2]) {
+    out[0] = out[1] = 0;
+    if(d_acc_rej.n == 2) d_acc_rej.download(out, 2);
+}
+
+// ============================================================================================ ExpectationValue
+
+static void scalar_sums(const SampleSet& S, bool with_eloc, bool with_lp, double* out4_dev, double* lp2_dev) {
+    k_scalar_sums<<<1, RED_T, 0, stream()>>>(S.weight.p, with_eloc ? S.eloc.p : nullptr, with_lp ? S.log_psi.p : nullptr, S.ns, out4_dev, lp2_dev);
+    ANGPU_CHECK_LAUNCH(); count_launch();
+}
+
+cplx ExpectationValue::value(const Operator& op, Psi& psi, Ensemble& ens) {
+    double f; cplx m; fluctuation(op, psi, ens, f, m); return m;
+}
+void ExpectationValue::fluctuation(const Operator& op, Psi& psi, Ensemble& ens, double& fluct, cplx& mean) {
+    ens.generate(psi, S);
+    psi.eloc(op, S);
+    d_scal.resize(8);
+    scalar_sums(S, true, false, d_scal.p, nullptr);
+    allreduce_sum(d_scal.p, 4);
+    double h[4]; d_scal.download(h, 4);
+    mean = cplx(h[0], h[1]);
+    fluct = std::sqrt(h[2] - abs2(mean));
+}
+
+// ============================================================================================ TDVP
+
+static unsigned pick_chunks(size_t ns, size_t col_blocks) {
+    // enough blocks to fill the GPU twice, chunk >= 32 samples, <= 128 chunks
+    const size_t want = ((size_t)ctx().num_sms * 8 + col_blocks - 1) / std::max<size_t>(1, col_blocks);
+    size_t ch = std::max<size_t>(1, std::min<size_t>(want, 128));
+    ch = std::min<size_t>(ch, std::max<size_t>(1, ns / 32));
+    return (unsigned)ch;
+}
+
+// mean_out / x_out: [P] device; X: per-sample complex factor
+static void col_reduce(TDVP& t, const cplx* X, cplx* mean_out, cplx* x_out) {
+    const size_t ns = t.S.ns; const unsigned P = t.P;
+    if(ns == 0) {
+        if(mean_out) ANGPU_CUDA(cudaMemsetAsync(mean_out, 0, sizeof(cplx) * P, stream()));
+        ANGPU_CUDA(cudaMemsetAsync(x_out, 0, sizeof(cplx) * P, stream()));
+        return;
+    }
+    unsigned chunks; size_t chunk;
+    if(t.factorised) {
+        const unsigned jb = ceil_div(t.rbm_M, 128), ib = ceil_div(t.rbm_N, RBM_IT);
+        chunks = pick_chunks(ns, (size_t)jb * ib); chunk = (ns + chunks - 1) / chunks; chunks = (unsigned)((ns + chunk - 1) / chunk);
+        t.chunk_buf.resize((size_t)2 * chunks * P);
+        cplx* pm = mean_out ? t.chunk_buf.p : nullptr; cplx* px = t.chunk_buf.p + (size_t)chunks * P;
+        k_col_reduce_rbm<<<dim3(jb, ib, chunks), 128, 0, stream()>>>(t.S.conf.p, t.T.p, t.S.weight.p, X, ns, t.rbm_N, t.rbm_M, t.words, chunk, pm, px);
+    } else {
+        const unsigned cb = ceil_div(P, 128);
+        chunks = pick_chunks(ns, cb); chunk = (ns + chunks - 1) / chunks; chunks = (unsigned)((ns + chunk - 1) / chunk);
+        t.chunk_buf.resize((size_t)2 * chunks * P);
+        cplx* pm = mean_out ? t.chunk_buf.p : nullptr; cplx* px = t.chunk_buf.p + (size_t)chunks * P;
+        k_col_reduce_dense<<<dim3(cb, chunks), 128, 0, stream()>>>(t.O.p, t.S.weight.p, X, ns, P, chunk, pm, px);
+    }
+    ANGPU_CHECK_LAUNCH(); count_launch();
+    if(mean_out) { k_sum_chunks<<<grid_for(P), 256, 0, stream()>>>(t.chunk_buf.p, chunks, P, mean_out); ANGPU_CHECK_LAUNCH(); count_launch(); }
+    k_sum_chunks<<<grid_for(P), 256, 0, stream()>>>(t.chunk_buf.p + (size_t)chunks * P, chunks, P, x_out);
+    ANGPU_CHECK_LAUNCH(); count_launch();
+}
+
+void TDVP::mark(int i) {
+    if(!profile) return;
+    if(!ev[i]) ANGPU_CUDA(cudaEventCreate(&ev[i]));
+    ANGPU_CUDA(cudaEventRecord(ev[i], stream()));
+}
+TDVP::~TDVP() { for(auto& e : ev) if(e) cudaEventDestroy(e); }
+
+void TDVP::eval(const Operator& op, Psi& psi, Ensemble& ens, bool want_S) {
+    ANGPU_REQUIRE(psi.P == P, "TDVP: num_params differs from the wavefunction's");
+    last_psi = &psi; words = psi.words; num_steps_global = ens.num_steps();
+    mark(0);
+    ens.generate(psi, S);
+    mark(1);
+    psi.eloc(op, S);
+    mark(2);
+    packed.resize(2 + 2 * (size_t)P);
+    scalar_sums(S, true, false, reinterpret_cast<double*>(packed.p), nullptr);
+    have_S = false;
+    if(psi.kind == Psi::RBM && !want_S) {
+        PsiRBM& rbm = static_cast<PsiRBM&>(psi);
+        rbm.compute_T(S, T);
+        factorised = true; have_dense_O = false; rbm_N = rbm.N; rbm_M = rbm.M;
+    } else {
+        O.resize(S.ns * (size_t)P);
+        psi.ok_rows(S, 0, S.ns, O.p);
+        factorised = false; have_dense_O = true;
+    }
+    col_reduce(*this, S.eloc.p, packed.p + 2, packed.p + 2 + P);
+    allreduce_sum(reinterpret_cast<double*>(packed.p), 2 * (2 + 2 * (size_t)P));
+    mark(3);
+    cplx h[2]; packed.download(h, 2);
+    E = h[0]; E2 = h[1].re; total_weight = h[1].im;
+    F.resize(P);
+    k_finalize_F<<<grid_for(P), 256, 0, stream()>>>(packed.p, P, F.p);
+    ANGPU_CHECK_LAUNCH(); count_launch();
+    evaluated = true;
+    mark(4);
+    if(profile) {
+        ANGPU_CUDA(cudaEventSynchronize(ev[4]));
+        for(int i = 0; i < 3; i++) ANGPU_CUDA(cudaEventElapsedTime(&phase_ms[i], ev[i], ev[i + 1]));
+        ANGPU_CUDA(cudaEventElapsedTime(&phase_ms[3], ev[0], ev[4]));
+    }
+    if(want_S) build_S();
+}
+
+void TDVP::ensure_dense_O(Psi* psi) {
+    if(have_dense_O) return;
+    ANGPU_REQUIRE(evaluated && psi, "TDVP: no samples (call eval first)");
+    O.resize(S.ns * (size_t)P);
+    psi->ok_rows(S, 0, S.ns, O.p);
+    have_dense_O = true;
+}
+
+void TDVP::build_S() {
+    ANGPU_REQUIRE(evaluated, "TDVP: call eval first");
+    ensure_dense_O(last_psi);
+    Smat.resize((size_t)P * P);
+    const unsigned nt = (P + ZT - 1) / ZT, tiles = nt * (nt + 1) / 2;
+    const size_t ns = S.ns;
+    // split the sample range when there are too few tiles to fill the GPU (bounded scratch: <= 1 GiB)
+    unsigned splits = 1;
+    if(ns > 0) {
+        const size_t want = ((size_t)ctx().num_sms * 2 + tiles - 1) / tiles;
+        const size_t mem_cap = std::max<size_t>(1, ((size_t)1 << 30) / (sizeof(cplx) * (size_t)P * P));
+        splits = (unsigned)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(want, mem_cap), std::max<size_t>(1, ns / ZK)));
+    }
+    const size_t chunk = ns ? (ns + splits - 1) / splits : 1;
+    splits = ns ? (unsigned)((ns + chunk - 1) / chunk) : 1;
+    const size_t stride = (size_t)P * P;
+    cplx* part = Smat.p;
+    if(splits > 1) { cg_buf.resize(stride * splits); part = cg_buf.p; }
+    if(ns) {
+        k_zherk<<<dim3(tiles, splits), 256, 0, stream()>>>(O.p, S.weight.p, ns, P, chunk, part, stride);
+        ANGPU_CHECK_LAUNCH(); count_launch();
+    } else Smat.zero();
+    if(splits > 1) {
+        k_S_finalize<<<grid_for(stride), 256, 0, stream()>>>(part, splits, stride, Ok_dev(), P, Smat.p, false);
+        ANGPU_CHECK_LAUNCH(); count_launch();
+    }
+    allreduce_sum(reinterpret_cast<double*>(Smat.p), 2 * stride);
+    k_S_finalize<<<grid_for(stride), 256, 0, stream()>>>(Smat.p, 1, stride, Ok_dev(), P, Smat.p, true);
+    ANGPU_CHECK_LAUNCH(); count_launch();
+    have_S = true;
+}
+
+void TDVP::S_dot_vector_dev(const cplx* v_dev, cplx* out_dev) {
+    ANGPU_REQUIRE(evaluated, "TDVP: call eval / eval_F first");
+    const size_t ns = S.ns;
+    row_a.resize(std::max<size_t>(1, ns));
+    if(ns) {
+        if(factorised) k_rowdot_rbm<<<ceil_div(ns, RBM_ST), 256, 0, stream()>>>(S.conf.p, T.p, v_dev, ns, rbm_N, rbm_M, words, row_a.p);
+        else k_rowdot_dense<<<(unsigned)ns, 256, 0, stream()>>>(O.p, v_dev, P, row_a.p);
+        ANGPU_CHECK_LAUNCH(); count_launch();
+    }
+    col_reduce(*this, row_a.p, nullptr, out_dev);
+    allreduce_sum(reinterpret_cast<double*>(out_dev), 2 * (size_t)P);
+    d_scal.resize(16);
+    cplx* dot = reinterpret_cast<cplx*>(d_scal.p) + 4;
+    k_dot<false><<<1, RED_T, 0, stream()>>>(Ok_dev(), v_dev, P, dot);
+    ANGPU_CHECK_LAUNCH(); count_launch();
+    k_sv_correct<<<grid_for(P), 256, 0, stream()>>>(Ok_dev(), dot, P, out_dev);
+    ANGPU_CHECK_LAUNCH(); count_launch();
+}
+void TDVP::S_dot_vector(const cplx* v_host, cplx* out_host) {
+    vec_in.upload(v_host, P);
+    vec_out.resize(P);
+    S_dot_vector_dev(vec_in.p, vec_out.p);
+    vec_out.download(out_host, P);
+}
+
+static void tdvp_diag(TDVP& t, DevBuf<double>& dbuf) {
+    dbuf.resize(t.P);
+    const size_t ns = t.S.ns;
+    if(t.factorised) k_diag_rbm<<<ceil_div(t.rbm_M, 128), 128, 0, stream()>>>(t.T.p, t.S.weight.p, ns, t.rbm_N, t.rbm_M, dbuf.p);
+    else k_diag_dense<<<ceil_div(t.P, 128), 128, 0, stream()>>>(t.O.p, t.S.weight.p, ns, t.P, dbuf.p);
+    ANGPU_CHECK_LAUNCH(); count_launch();
+    allreduce_sum(dbuf.p, t.P);
+    k_diag_finalize<<<grid_for(t.P), 256, 0, stream()>>>(dbuf.p, t.Ok_dev(), t.P);
+    ANGPU_CHECK_LAUNCH(); count_launch();
+}
+
+int TDVP::solve_cg(double tol, unsigned max_iter, double shift_abs, double shift_rel, cplx rhs_phase, cplx* x_host, double* rel_res_out) {
+    ANGPU_REQUIRE(evaluated, "TDVP: call eval / eval_F first");
+    const size_t n = P;
+    DevBuf<double> dg;
+    if(shift_rel != 0.0) tdvp_diag(*this, dg); else { dg.resize(n); dg.zero(); }
+    cg_buf.resize(5 * n);                                     // x | r | p | Ap | b
+    cplx *x = cg_buf.p, *r = x + n, *p = r + n, *Ap = p + n, *b = Ap + n;
+    d_scal.resize(16);
+    cplx* scal = reinterpret_cast<cplx*>(d_scal.p);
+    ANGPU_CUDA(cudaMemsetAsync(x, 0, sizeof(cplx) * n, stream()));
+    k_scale_vec<<<grid_for(n), 256, 0, stream()>>>(F.p, rhs_phase, b, n, false);
+    ANGPU_CUDA(cudaMemcpyAsync(r, b, sizeof(cplx) * n, cudaMemcpyDeviceToDevice, stream()));
+    ANGPU_CUDA(cudaMemcpyAsync(p, b, sizeof(cplx) * n, cudaMemcpyDeviceToDevice, stream()));
+    k_dot<true><<<1, RED_T, 0, stream()>>>(r, r, n, scal + 0);
+    count_launch(2);
+    cplx h; ANGPU_CUDA(cudaMemcpyAsync(&h, scal, sizeof(cplx), cudaMemcpyDeviceToHost, stream()));
+    ANGPU_CUDA(cudaStreamSynchronize(stream()));
+    const double b2 = h.re;
+    if(rel_res_out) *rel_res_out = 0.0;
+    unsigned it = 0;
+    if(b2 > 0.0) {
+        const unsigned check_every = 8;
+        for(it = 1; it <= max_iter; it++) {
+            S_dot_vector_dev(p, Ap);
+            k_add_shift<<<grid_for(n), 256, 0, stream()>>>(Ap, p, dg.p, shift_abs, shift_rel, n);
+            k_dot<true><<<1, RED_T, 0, stream()>>>(p, Ap, n, scal + 1);
+            k_cg_xr<<<grid_for(n), 256, 0, stream()>>>(x, r, p, Ap, scal, n);
+            k_dot<true><<<1, RED_T, 0, stream()>>>(r, r, n, scal + 2);
+            k_cg_p<<<grid_for(n), 256, 0, stream()>>>(p, r, scal, n);
+            k_cg_roll<<<1, 1, 0, stream()>>>(scal);
+            ANGPU_CHECK_LAUNCH(); count_launch(6);
+            if(it % check_every == 0 || it == max_iter) {
+                ANGPU_CUDA(cudaMemcpyAsync(&h, scal, sizeof(cplx), cudaMemcpyDeviceToHost, stream()));
+                ANGPU_CUDA(cudaStreamSynchronize(stream()));
+                if(rel_res_out) *rel_res_out = std::sqrt(h.re / b2);
+                if(h.re <= tol * tol * b2) break;
+            }
+        }
+        if(it > max_iter) it = max_iter;
+    }
+    ANGPU_CUDA(cudaMemcpyAsync(x_host, x, sizeof(cplx) * n, cudaMemcpyDeviceToHost, stream()));
+    ANGPU_CUDA(cudaStreamSynchronize(stream()));
+    return (int)it;
+}
+
+static cusolverDnHandle_t g_cusolver = nullptr;
+void TDVP::solve_dense(double shift_abs, double shift_rel, cplx rhs_phase, cplx* x_host) {
+    ANGPU_REQUIRE(evaluated, "TDVP: call eval first");
+    if(!have_S) build_S();
+    const size_t n = P;
+    DevBuf<double> dg;
+    if(shift_rel != 0.0) tdvp_diag(*this, dg); else { dg.resize(n); dg.zero(); }
+    // row-major Hermitian S read as column-major is conj(S): solve conj(S) y = conj(b), x = conj(y)
+    DevBuf<cplx> A(n * n), b(n);
+    A.copy_from(Smat);
+    k_add_diag_shift<<<grid_for(n), 256, 0, stream()>>>(A.p, dg.p, shift_abs, shift_rel, P);
+    k_scale_vec<<<grid_for(n), 256, 0, stream()>>>(F.p, rhs_phase, b.p, n, false);
+    k_conj_inplace<<<grid_for(n), 256, 0, stream()>>>(b.p, n);
+    ANGPU_CHECK_LAUNCH(); count_launch(3);
+    if(!g_cusolver) { if(cusolverDnCreate(&g_cusolver) != CUSOLVER_STATUS_SUCCESS) throw Error("cusolverDnCreate failed"); }
+    cusolverDnSetStream(g_cusolver, stream());
+    int lwork = 0;
+    auto* Ad = reinterpret_cast<cuDoubleComplex*>(A.p); auto* bd = reinterpret_cast<cuDoubleComplex*>(b.p);
+    if(cusolverDnZpotrf_bufferSize(g_cusolver, CUBLAS_FILL_MODE_LOWER, (int)n, Ad, (int)n, &lwork) != CUSOLVER_STATUS_SUCCESS) throw Error("Zpotrf_bufferSize failed");
+    DevBuf<cplx> work((size_t)lwork); DevBuf<int> info(1);
+    if(cusolverDnZpotrf(g_cusolver, CUBLAS_FILL_MODE_LOWER, (int)n, Ad, (int)n, reinterpret_cast<cuDoubleComplex*>(work.p), lwork, info.p) != CUSOLVER_STATUS_SUCCESS) throw Error("Zpotrf failed");
+    int hinfo = 0; info.download(&hinfo, 1);
+    if(hinfo != 0) throw Error("dense solve: S + shift is not positive definite (Zpotrf info = " + std::to_string(hinfo) + "); increase the diagonal shift");
+    if(cusolverDnZpotrs(g_cusolver, CUBLAS_FILL_MODE_LOWER, (int)n, 1, Ad, (int)n, bd, (int)n, info.p) != CUSOLVER_STATUS_SUCCESS) throw Error("Zpotrs failed");
+    k_conj_inplace<<<grid_for(n), 256, 0, stream()>>>(b.p, n);
+    ANGPU_CHECK_LAUNCH(); count_launch();
+    b.download(x_host, n);
+}
+
+// ============================================================================================ FP64 peak probe
+// Dependent-free DFMA streams: 8 independent accumulators per thread, 64k FMAs each. Used by bench.py as the measured
+// denominator for the FP64-pipe-bound kernels (MEASURED_PEAKS.json has no fp64 figure).
+__global__ void __launch_bounds__(256) k_fp64_peak(double* out, double a, double b, int iters) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for(int i = 0; i < iters; i++) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+double measure_fp64_tflops() {
+    const int blocks = ctx().num_sms * 8, threads = 256, iters = 8192;
+    DevBuf<double> out((size_t)blocks * threads);
+    cudaEvent_t e0, e1;
+    ANGPU_CUDA(cudaEventCreate(&e0)); ANGPU_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for(int rep = 0; rep < 5; rep++) {
+        ANGPU_CUDA(cudaEventRecord(e0, stream()));
+        k_fp64_peak<<<blocks, threads, 0, stream()>>>(out.p, 0.999999, 1e-7, iters);
+        ANGPU_CUDA(cudaEventRecord(e1, stream()));
+        ANGPU_CUDA(cudaEventSynchronize(e1));
+        float ms; ANGPU_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if(rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    const double flops = 2.0 * 8.0 * iters * (double)blocks * threads;
+    return flops / (best * 1e-3) / 1e12;
+}
+
+// ============================================================================================ free functions
+
+void scalar_sums_eloc(const SampleSet& S, double* out4_dev) { scalar_sums(S, true, false, out4_dev, nullptr); }
+void enumerate_probe(uint64_t index, unsigned words, uint64_t* host_out) {
+    DevBuf<uint64_t> d(words);
+    k_enumerate<<<1, 32, 0, stream()>>>(d.p, (size_t)index, 1, words);
+    ANGPU_CHECK_LAUNCH(); count_launch();
+    d.download(host_out, words);
+}
+
+cplx log_psi_s(Psi& psi, const uint64_t* conf) {
+    SampleSet S; S.resize(1, psi.words);
+    S.conf.upload(conf, psi.words);
+    psi.log_psi(S, false);
+    cplx r; S.log_psi.download(&r, 1);
+    return r;
+}
+void psi_O_k(Psi& psi, const uint64_t* conf, cplx* out_host) {
+    SampleSet S; S.resize(1, psi.words);
+    S.conf.upload(conf, psi.words);
+    DevBuf<cplx> row(psi.P);
+    psi.ok_rows(S, 0, 1, row.p);
+    row.download(out_host, psi.P);
+}
+void log_psi_vector(Psi& psi, Ensemble& ens, cplx* out_host, bool exponentiate) {
+    SampleSet S;
+    ens.generate(psi, S);
+    if(exponentiate && S.ns) { k_exp_inplace<<<grid_for(S.ns), 256, 0, stream()>>>(S.log_psi.p, S.ns); ANGPU_CHECK_LAUNCH(); count_launch(); }
+    S.log_psi.download(out_host, S.ns);
+}
+cplx log_psi_mean(Psi& psi, Ensemble& ens) {
+    SampleSet S;
+    ens.generate(psi, S);
+    DevBuf<double> d(8);
+    scalar_sums(S, false, true, nullptr, d.p);
+    allreduce_sum(d.p, 2);
+    double h[2]; d.download(h, 2);
+    return cplx(h[0], h[1]);
+}
+double psi_norm(Psi& psi, Ensemble& es) {
+    ANGPU_REQUIRE(!es.is_mc, "psi_norm needs an ExactSummation ensemble");
+    SampleSet S;
+    es.generate(psi, S);
+    DevBuf<double> d(8);
+    scalar_sums(S, false, false, d.p, nullptr);
+    allreduce_sum(d.p, 4);
+    double h[4]; d.download(h, 4);
+    return std::sqrt(h[3]);
+}
+void psi_O_k_vector(Psi& psi, Ensemble& es, cplx* out_host) {
+    SampleSet S;
+    es.generate(psi, S);
+    DevBuf<cplx> O(std::max<size_t>(1, S.ns * (size_t)psi.P)), out(psi.P);
+    psi.ok_rows(S, 0, S.ns, O.p);
+    k_sum_rows<<<ceil_div(psi.P, 128), 128, 0, stream()>>>(O.p, S.ns, psi.P, out.p);
+    ANGPU_CHECK_LAUNCH(); count_launch();
+    allreduce_sum(reinterpret_cast<double*>(out.p), 2 * (size_t)psi.P);
+    out.download(out_host, psi.P);
+}
+void apply_operator(Psi& psi, const Operator& op, Ensemble& ens, cplx* out_host) {
+    SampleSet S;
+    ens.generate(psi, S);
+    psi.eloc(op, S);
+    DevBuf<cplx> out(std::max<size_t>(1, S.ns));
+    if(S.ns) { k_mul_exp<<<grid_for(S.ns), 256, 0, stream()>>>(S.log_psi.p, S.eloc.p, out.p, S.ns); ANGPU_CHECK_LAUNCH(); count_launch(); }
+    out.download(out_host, S.ns);
+}
+void local_energies(Psi& psi, const Operator& op, const uint64_t* confs_host, size_t ns, cplx* log_psi_out, cplx* eloc_out) {
+    SampleSet S; S.resize(ns, psi.words);
+    S.conf.upload(confs_host, ns * psi.words);
+    psi.log_psi(S, false);
+    psi.eloc(op, S);
+    if(log_psi_out) S.log_psi.download(log_psi_out, ns);
+    if(eloc_out) S.eloc.download(eloc_out, ns);
+}
+
+} // namespace angpu

@@ -1,0 +1,112 @@
+// Ensembles and "network functions" (ExpectationValue, TDVP, probes) of the VMC hot path.
+//
+// Structure (differs from the reference by design):  every functional is
+//     generate samples -> per-sample kernels (E_loc, O_k) -> deterministic partial sums on the device
+//     -> [all-reduce hook, one packed buffer] -> finalise on the device -> copy out on request.
+// The reference instead fuses a consumer lambda into one kernel per ensemble.foreach and reduces with global
+// fp64 atomics from every block into single addresses (ExpectationValue.cu.template:43,259-260;
+// TDVP.cu.template:107-121, 260-263).
+#pragma once
+#include "psi.hpp"
+
+namespace angpu {
+
+// Multi-GPU: sum `count` doubles in place across ranks, stream-ordered on angpu's stream.
+// Registered by the host layer (torch.distributed / NCCL); null => single process.
+typedef void (*allreduce_fn)(void* dev_ptr, unsigned long long count, void* user);
+void set_allreduce(allreduce_fn fn, void* user);
+void allreduce_sum(double* dev_ptr, size_t count);
+
+struct Ensemble {
+    bool is_mc = false;
+    // ExactSummation (include/ensembles/ExactSummation.hpp)
+    unsigned num_sites = 0;
+    // MonteCarlo (include/ensembles/MonteCarlo.hpp, source/ensembles/MonteCarlo.cu:14-42)
+    unsigned long long num_samples = 0;
+    unsigned num_sweeps = 0, num_therm = 0, num_chains = 0, call = 0;
+    uint64_t seed = 0xA11CE;
+    // sharding: this process owns chains / basis indices [begin, begin+count) of the global range
+    unsigned rank = 0, world = 1;
+    DevBuf<unsigned long long> d_acc_rej;
+
+    size_t num_steps() const { return is_mc ? (size_t)num_samples : ((size_t)1 << num_sites); }
+    void shard(size_t total, size_t& begin, size_t& count) const {
+        begin = total * rank / world;
+        count = total * (rank + 1) / world - begin;
+    }
+    size_t local_steps() const {
+        size_t b, c;
+        if(is_mc) { shard(num_chains, b, c); return c * (size_t)(num_samples / num_chains); }
+        shard(num_steps(), b, c); return c;
+    }
+    // fills S.conf / S.log_psi / S.weight for this process' share
+    void generate(Psi& psi, SampleSet& S);
+    void acceptance(unsigned long long out[2]);
+};
+
+struct ExpectationValue {
+    SampleSet S;
+    DevBuf<double> d_scal;
+    // <A>  (ExpectationValue.cu.template:20-50)
+    cplx value(const Operator& op, Psi& psi, Ensemble& ens);
+    // (sqrt(<|A_loc|^2> - |<A>|^2), <A>)  (:176-216)
+    void fluctuation(const Operator& op, Psi& psi, Ensemble& ens, double& fluct, cplx& mean);
+};
+
+struct TDVP {
+    unsigned P;
+    double threshold = -1e6;                 // kept for API parity (include/network_functions/TDVP.hpp:35)
+    SampleSet S;
+    // packed partial sums, all-reduced as ONE buffer: [0] = sum w E, [1] = (sum w |E|^2, sum w),
+    // [2 .. 2+P) = sum w O_k, [2+P .. 2+2P) = sum w E conj(O_k)
+    DevBuf<cplx> packed;
+    DevBuf<cplx> F;                          // F_k = <E O_k*> - <E><O_k>*
+    DevBuf<cplx> Smat;                       // P x P row-major, S = <O_k* O_k'> - <O_k>*<O_k'>
+    DevBuf<cplx> O;                          // dense O_k_samples [ns][P] (valid iff have_dense_O)
+    DevBuf<cplx> T;                          // PsiRBM factorised form [ns][M] (valid iff factorised)
+    DevBuf<cplx> chunk_buf, row_a, vec_in, vec_out, cg_buf;
+    DevBuf<double> d_scal;
+    bool have_dense_O = false, factorised = false, have_S = false, evaluated = false;
+    unsigned rbm_N = 0, rbm_M = 0, words = 1;
+    cplx E{0.0, 0.0}; double E2 = 0.0, total_weight = 0.0;
+    unsigned long long num_steps_global = 0;
+
+    explicit TDVP(unsigned P_) : P(P_) {}
+    const cplx* Ok_dev() const { return packed.p + 2; }
+    // TDVP::eval (TDVP.cu.template:182-302): E, E2, <O_k>, F, O_k_samples, S.
+    void eval(const Operator& op, Psi& psi, Ensemble& ens, bool want_S);
+    // TDVP::eval_F_vector (:306-334).  For PsiRBM the samples are kept in factorised form unless dense rows are requested.
+    void eval_F(const Operator& op, Psi& psi, Ensemble& ens) { eval(op, psi, ens, false); }
+    double var_H() const { return E2 - abs2(E); }
+    void ensure_dense_O(Psi* psi);
+    // out = S v using the samples of the last eval (TDVP::S_dot_vector, :337-443), O(ns*P) instead of the reference's O(ns*P^2)
+    void S_dot_vector_dev(const cplx* v_dev, cplx* out_dev);
+    void S_dot_vector(const cplx* v_host, cplx* out_host);
+    // NEW (no reference counterpart): solve (S + shift_abs*I + shift_rel*diag(S)) x = rhs_phase * F
+    int  solve_cg(double tol, unsigned max_iter, double shift_abs, double shift_rel, cplx rhs_phase, cplx* x_host, double* rel_res_out);
+    void solve_dense(double shift_abs, double shift_rel, cplx rhs_phase, cplx* x_host);
+    void build_S();
+    Psi* last_psi = nullptr;
+    // optional phase timing (bench.py): CUDA events on the library stream around sample / E_loc / O_k+reduce
+    bool profile = false;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    float phase_ms[4] = {0, 0, 0, 0};     // sample, eloc, ok+reduce(+allreduce), total
+    void mark(int i);
+    ~TDVP();
+};
+
+// free functions (source/network_functions/{PsiVector,PsiNorm,PsiOkVector,ApplyOperator}.cu.template)
+cplx   log_psi_s(Psi& psi, const uint64_t* conf);
+void   psi_O_k(Psi& psi, const uint64_t* conf, cplx* out_host);
+void   log_psi_vector(Psi& psi, Ensemble& ens, cplx* out_host, bool exponentiate);
+cplx   log_psi_mean(Psi& psi, Ensemble& ens);
+double psi_norm(Psi& psi, Ensemble& es);
+void   psi_O_k_vector(Psi& psi, Ensemble& es, cplx* out_host);
+void   apply_operator(Psi& psi, const Operator& op, Ensemble& ens, cplx* out_host);
+// helpers for the C ABI
+void   scalar_sums_eloc(const SampleSet& S, double* out4_dev);
+void   enumerate_probe(uint64_t index, unsigned words, uint64_t* host_out);
+double measure_fp64_tflops();
+void   local_energies(Psi& psi, const Operator& op, const uint64_t* confs_host, size_t ns, cplx* log_psi_out, cplx* eloc_out);
+
+} // namespace angpu

@@ -1,0 +1,85 @@
+"""Shared test helpers: build the same model in the product (annongpu_b200), the CPU oracle (oracle.port_oracle)
+and the compiled reference (oracle.ref_oracle) from one spec of annongpu_b200.factories."""
+import numpy as np
+
+from annongpu_b200 import factories as F
+
+
+def make_psi(mod, spec, log_prefactor=None):
+    """mod: annongpu_b200 | oracle.port_oracle | oracle.ref_oracle."""
+    lp = spec.log_prefactor if log_prefactor is None else log_prefactor
+    if isinstance(spec, F.RBMSpec):
+        return mod.PsiRBM(spec.W, spec.final_weight, lp)
+    if isinstance(spec, F.DeepSpec):
+        return mod.PsiDeep(spec.num_sites, spec.input_weights, spec.biases, spec.connections, spec.weights, spec.final_weights, lp)
+    if isinstance(spec, F.CNNSpec):
+        return mod.PsiCNN(spec.extent, spec.num_channels_list, spec.connectivity_list, spec.symmetry_classes, spec.params,
+                          spec.final_factor, lp)
+    raise TypeError(spec)
+
+
+def make_op(mod, H, words=None):
+    name = mod.__name__
+    words = words or H.words
+    c, a, b = H.arrays(words)
+    if name.endswith("ref_oracle"):
+        assert words == 1
+        return mod.Operator(c, a[:, 0], b[:, 0])
+    if name.endswith("port_oracle"):
+        return mod.Operator(c, a, b, words)
+    return mod.Operator(H)
+
+
+def make_classical(mod, num_sites, order, local_ops, params, ref_spec, log_prefactor):
+    """local_ops: list of PauliSum; ref_spec: CNNSpec or None."""
+    name = mod.__name__
+    ops = [make_op(mod, h) for h in local_ops]
+    psi_ref = make_psi(mod, ref_spec) if ref_spec is not None else None
+    if name.endswith("oracle"):
+        psi = mod.PsiClassical(num_sites, order, ops, params, psi_ref, log_prefactor)
+    else:
+        cls = {(1, False): mod.PsiClassicalFP_1, (2, False): mod.PsiClassicalFP_2,
+               (1, True): mod.PsiClassicalANN_1, (2, True): mod.PsiClassicalANN_2}[(order, ref_spec is not None)]
+        psi = cls(num_sites, ops, params, psi_ref if psi_ref is not None else mod.PsiFullyPolarized(num_sites, log_prefactor),
+                  log_prefactor)
+    psi._keepalive = (ops, psi_ref)
+    return psi
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    scale = max(np.abs(b).max() if b.size else 0.0, 1e-300)
+    return float(np.abs(a - b).max() / scale) if a.size else 0.0
+
+
+# ---------------------------------------------------------------- small model zoo used by the parity tests
+
+def zoo():
+    """name -> (spec or classical-builder args, Hamiltonian PauliSum, num_sites). Sizes the oracle finishes in seconds."""
+    z = {}
+    z["rbm10"] = (F.rbm_spec(10, 20, noise=5e-2, final_weight=10, seed=1), F.heisenberg(10, F.ring_bonds(10)), 10)
+    z["rbm8_cfw"] = (F.rbm_spec(8, 24, noise=5e-2, final_weight=2.0 - 0.5j, seed=11), F.tfim(8, F.ring_bonds(8), h=0.8), 8)
+    z["rbm12_m40"] = (F.rbm_spec(12, 40, noise=3e-2, final_weight=3, seed=12), F.heisenberg(12, F.ring_bonds(12)), 12)
+    z["deep1"] = (F.deep_spec(6, 6, [12], [6], noise=1e-2, a=0, final_weights=2, seed=4), F.heisenberg(6, F.ring_bonds(6)), 6)
+    z["deep2"] = (F.deep_spec(8, 8, [16, 8], [4, 8], noise=1e-2, a=0.1, final_weights=3, seed=2), F.tfim(8, F.ring_bonds(8), h=0.7), 8)
+    z["deep3"] = (F.deep_spec(6, 6, [18, 9, 3], [3, 2, 3], noise=1e-2, a=0, final_weights=2, seed=3), F.heisenberg(6, F.ring_bonds(6)), 6)
+    z["cnn"] = (F.cnn_spec([2, 2, 3], [(2, [2, 2, 2]), (3, [1, 2, 2])], noise=1e-1, final_factor=2, seed=5),
+                F.heisenberg(12, F.ring_bonds(12)), 12)
+    z["cnn_sym"] = (F.cnn_spec([3, 4], [(2, [2, 3]), (2, [3, 2]), (1, [2, 2])], noise=1e-1, final_factor=2, seed=6,
+                               symmetry_classes=np.array([0, 1] * 6)), F.tfim(12, F.square_lattice_bonds(3, 4)), 12)
+    return z
+
+
+def classical_zoo():
+    N = 6
+    Hl = [F.PauliSum(N).add(1.0, {i: "Z", (i + 1) % N: "Z"}).add(0.3, {i: "X"}).add(0.2j, {i: "Y", (i + 2) % N: "Z"}) for i in range(N)]
+    rng = np.random.default_rng(7)
+    pr = 0.1 * (rng.normal(size=N) + 1j * rng.normal(size=N))
+    ref_spec = F.cnn_spec([1, 2, 3], [(2, [1, 2, 2])], noise=1e-1, final_factor=2, seed=8)
+    H = F.heisenberg(N, F.ring_bonds(N))
+    return {
+        "clfp1": (N, 1, Hl, pr, None, -1.0, H),
+        "clfp2": (N, 2, Hl, pr, None, -1.0, H),
+        "clann1": (N, 1, Hl, pr, ref_spec, 0.0, H),
+        "clann2": (N, 2, Hl, pr, ref_spec, 0.0, H),
+    }
