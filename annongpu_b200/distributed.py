@@ -1,0 +1,58 @@
+"""Multi-GPU plumbing: one process per GPU, `torch.distributed` for the collectives.
+
+The hot path shards with no data-path exchange: Markov chains (and ExactSummation basis ranges) are independent, so
+rank r of G owns the chains / indices [r*n/G, (r+1)*n/G) — Philox streams are keyed by the GLOBAL chain id, so the
+sampled configurations do not depend on G.  The only communication is the sum of the packed partial sums
+{sum w E, sum w |E|^2, sum w, sum w O_k, sum w E O_k*} (one all-reduce per functional), the S-matrix partial
+(dense SR) or one P-vector per CG iteration (matrix-free SR).  libangpu calls back into `allreduce_hook` at those
+points; the hook wraps the device pointer in a torch tensor (no copy) and runs `dist.all_reduce` on it.
+
+The reference has no counterpart (single device, no collectives — SURVEY.md §2).
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+from . import api
+
+
+class _DevArray:
+    """Zero-copy view of `count` float64 at a raw CUDA device pointer."""
+
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+
+
+def shard_range(total, rank, world):
+    """The C ABI's partition (Ensemble::shard in csrc/vmc.hpp): [total*rank//world, total*(rank+1)//world)."""
+    begin = total * rank // world
+    return begin, total * (rank + 1) // world - begin
+
+
+def allreduce_hook(ptr, count):
+    t = torch.as_tensor(_DevArray(ptr, count), device=torch.device("cuda", torch.cuda.current_device()))
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+
+def init_from_env(backend="nccl"):
+    """Reads RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* (torchrun). Returns (rank, world). Single process: (0, 1)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    api.setDevice(local_rank)
+    # run the library on torch's current stream so that NCCL work and torch.cuda.Event timing are ordered with it
+    api.set_stream(torch.cuda.current_stream().cuda_stream)
+    if world > 1:
+        if not dist.is_initialized():
+            dist.init_process_group(backend=backend, rank=rank, world_size=world,
+                                    device_id=torch.device("cuda", local_rank))
+        api.set_allreduce(allreduce_hook)
+    return rank, world
+
+
+def shutdown():
+    api.set_allreduce(None)
+    if dist.is_initialized():
+        dist.destroy_process_group()

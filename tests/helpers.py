@@ -35,6 +35,9 @@ def make_classical(mod, num_sites, order, local_ops, params, ref_spec, log_prefa
     name = mod.__name__
     ops = [make_op(mod, h) for h in local_ops]
     psi_ref = make_psi(mod, ref_spec) if ref_spec is not None else None
+    if psi_ref is not None and hasattr(psi_ref, "init_gradient"):
+        # the reference copies psi_ref (with its per-sample angle scratch) into PsiClassical: size it first
+        psi_ref.init_gradient(1 << num_sites)
     if name.endswith("oracle"):
         psi = mod.PsiClassical(num_sites, order, ops, params, psi_ref, log_prefactor)
     else:
@@ -83,3 +86,39 @@ def classical_zoo():
         "clann1": (N, 1, Hl, pr, ref_spec, 0.0, H),
         "clann2": (N, 2, Hl, pr, ref_spec, 0.0, H),
     }
+
+
+class GpuAdapter:
+    """Presents annongpu_b200 with the oracle modules' function names, so one checker serves both."""
+    __name__ = "annongpu_b200"
+
+    def __init__(self, A):
+        self.A = A
+        self.ev = A.ExpectationValue(True)
+        for k in ("PsiRBM", "PsiDeep", "PsiCNN", "PsiClassicalFP_1", "PsiClassicalFP_2", "PsiClassicalANN_1", "PsiClassicalANN_2",
+                  "PsiFullyPolarized", "Operator", "log_psi", "psi_vector", "apply_operator"):
+            setattr(self, k, getattr(A, k))
+
+    def ExactSummation(self, N):
+        return self.A.ExactSummationSpins(N, True)
+
+    def psi_norm(self, psi, es):
+        return psi.norm(es)
+
+    def expectation(self, op, psi, ens):
+        return self.ev(op, psi, ens)
+
+    def fluctuation(self, op, psi, ens):
+        return self.ev.fluctuation(op, psi, ens)
+
+    def gradient(self, op, psi, ens):
+        return self.ev.gradient(op, psi, ens)
+
+    def TDVP(self, P):
+        return self.A.TDVP(P, True)
+
+    def log_psi_s(self, psi, conf):
+        return self.A.log_psi_s(psi, np.asarray(conf, dtype=np.uint64))
+
+    def psi_O_k(self, psi, conf):
+        return self.A.psi_O_k(psi, np.asarray(conf, dtype=np.uint64))
