@@ -90,6 +90,7 @@ _SIGNATURES = {
     "angpu_tdvp_S_dot_vector": [vp, vp, vp],
     "angpu_tdvp_solve_cg": [vp, dbl, u32, dbl, dbl, vp, vp, vp, vp],
     "angpu_tdvp_solve_dense": [vp, dbl, dbl, vp, vp],
+    "angpu_tdvp_build_S_tensorcore": [vp],
     "angpu_tdvp_set_profile": [vp, i32],
     "angpu_tdvp_phase_ms": [vp, vp],
     "angpu_measure_fp64_tflops": [vp],

@@ -64,7 +64,12 @@ def setDevice(device):
 
 
 def set_stream(cuda_stream):
-    call("angpu_set_stream", C.c_void_p(int(cuda_stream)) if cuda_stream else None)
+    """Run the library on the given CUDA stream handle; None restores the library's own stream.  Handle 0 (the legacy
+    default stream, what torch.cuda.default_stream().cuda_stream returns) is passed as cudaStreamLegacy."""
+    if cuda_stream is None:
+        call("angpu_set_stream", None)
+    else:
+        call("angpu_set_stream", C.c_void_p(int(cuda_stream) or 1))
 
 
 def synchronize():
@@ -671,15 +676,20 @@ class TDVP:
         call("angpu_tdvp_S_dot_vector", self._h, _p(vec), _p(out))
         return out
 
+    def build_S_tensorcore(self):
+        """NEW, opt-in: rebuild S on the tcgen05 tensor cores (3xTF32, ~1e-5 relative to ||S||); then S_matrix / solve use it."""
+        call("angpu_tdvp_build_S_tensorcore", self._h)
+
     def set_profile(self, enable=True):
         call("angpu_tdvp_set_profile", self._h, 1 if enable else 0)
 
     @property
     def phase_ms(self):
         """{sample, eloc, ok_reduce, total} device milliseconds of the last eval / eval_F (needs set_profile(True))."""
-        out = np.empty(4)
+        out = np.empty(6)
         call("angpu_tdvp_phase_ms", self._h, _p(out))
-        return dict(sample=float(out[0]), eloc=float(out[1]), ok_reduce=float(out[2]), total=float(out[3]))
+        return dict(sample=float(out[0]), eloc=float(out[1]), ok_reduce=float(out[2]), total=float(out[3]),
+                    s_build=float(out[4]), solve=float(out[5]))
 
     def solve_cg(self, tol=1e-6, max_iter=1000, shift_abs=0.0, shift_rel=1e-3, rhs_phase=1.0):
         """NEW: matrix-free CG for (S + shift_abs I + shift_rel diag S) x = rhs_phase F. Returns (x, iterations, rel_residual)."""

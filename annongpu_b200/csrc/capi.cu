@@ -298,8 +298,9 @@ int angpu_tdvp_solve_cg(angpu_tdvp_t tdvp, double tol, unsigned max_iter, double
     if(rel_residual_out) *rel_residual_out = rr;
     API_END
 }
+int angpu_tdvp_build_S_tensorcore(angpu_tdvp_t tdvp) { API_BEGIN NOTNULL(tdvp); tdvp->t->build_S_tensorcore(); API_END }
 int angpu_tdvp_set_profile(angpu_tdvp_t tdvp, int enable) { API_BEGIN NOTNULL(tdvp); tdvp->t->profile = enable != 0; API_END }
-int angpu_tdvp_phase_ms(angpu_tdvp_t tdvp, double out[4]) { API_BEGIN NOTNULL(tdvp); NOTNULL(out); for(int i = 0; i < 4; i++) out[i] = tdvp->t->phase_ms[i]; API_END }
+int angpu_tdvp_phase_ms(angpu_tdvp_t tdvp, double out[6]) { API_BEGIN NOTNULL(tdvp); NOTNULL(out); for(int i = 0; i < 6; i++) out[i] = tdvp->t->phase_ms[i]; API_END }
 int angpu_measure_fp64_tflops(double* out) { API_BEGIN NOTNULL(out); *out = measure_fp64_tflops(); API_END }
 int angpu_tdvp_solve_dense(angpu_tdvp_t tdvp, double shift_abs, double shift_rel, const double rhs_phase[2], double* x_out) {
     API_BEGIN NOTNULL(tdvp); NOTNULL(rhs_phase); NOTNULL(x_out); tdvp->t->solve_dense(shift_abs, shift_rel, c2(rhs_phase), cp(x_out)); API_END

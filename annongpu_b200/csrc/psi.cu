@@ -101,6 +101,13 @@ void PsiRBM::upload() {
     std::vector<cplx> t((size_t)N * M);
     for(unsigned i = 0; i < N; i++) for(unsigned j = 0; j < M; j++) t[(size_t)j * N + i] = hW[(size_t)i * M + j];
     dWt.upload(t);
+    // rows padded to 32*K complex for the register-resident sampler (rbm_kernels.cuh: k_mc_rbm)
+    if(M <= 512u) {
+        const unsigned Mp = 32u * (M <= 32u ? 1u : M <= 64u ? 2u : M <= 128u ? 4u : M <= 256u ? 8u : 16u);
+        std::vector<cplx> wp((size_t)N * Mp, cplx(0.0, 0.0));
+        for(unsigned i = 0; i < N; i++) for(unsigned j = 0; j < M; j++) wp[(size_t)i * Mp + j] = hW[(size_t)i * M + j];
+        dWpad.upload(wp);
+    }
 }
 void PsiRBM::log_psi(SampleSet& S, bool es_weights) {
     if(S.ns == 0) return;
@@ -128,8 +135,16 @@ void PsiRBM::eloc(const Operator& op, SampleSet& S) {
     unsigned wpb = (unsigned)std::min<size_t>(8, budget / slice);
     while(wpb > 1 && wpb * slice > budget / 2) wpb--;
     const unsigned grid = (unsigned)std::min<size_t>((S.ns + wpb - 1) / wpb, (size_t)ctx().num_sms * 16);
-    set_smem(k_eloc_rbm, wpb * slice);
-    k_eloc_rbm<<<grid, wpb * 32, wpb * slice, stream()>>>(dev(), op.dev, S.conf.p, S.angles.p, S.ns, S.eloc.p);
+    auto launch = [&](auto kernel) {
+        set_smem(kernel, wpb * slice);
+        kernel<<<grid, wpb * 32, wpb * slice, stream()>>>(dev(), op.dev, S.conf.p, S.angles.p, S.ns, S.eloc.p);
+    };
+    switch(op.dev.max_flips) {
+        case 0: case 1: launch(k_eloc_rbm<1>); break;
+        case 2: launch(k_eloc_rbm<2>); break;
+        case 3: launch(k_eloc_rbm<3>); break;
+        default: launch(k_eloc_rbm<4>); break;
+    }
     ANGPU_CHECK_LAUNCH(); count_launch();
 }
 void PsiRBM::compute_T(SampleSet& S, DevBuf<cplx>& T) {
@@ -150,25 +165,38 @@ void PsiRBM::ok_rows(SampleSet& S, size_t s0, size_t cnt, cplx* out) {
     ANGPU_CUDA(cudaStreamSynchronize(stream()));   // T is freed on return
 }
 
-template<int K>
-static void launch_mc_rbm(const RbmDev& d, const McParams& mc, SampleSet& S, unsigned long long* acc_rej_dev) {
-    const unsigned wpb = 4, grid = ceil_div(mc.num_chains_local, wpb);
+template<int K, int WORDS>
+static void launch_mc_rbm(const RbmDev& d, const cplx* Wp, const McParams& mc, SampleSet& S, unsigned long long* acc_rej_dev) {
+    const unsigned wpb = MC_RBM_THREADS / 32, grid = ceil_div(mc.num_chains_local, wpb);
     if(d.fw.im == 0.0)
-        k_mc_rbm<K, true><<<grid, wpb * 32, 0, stream()>>>(d, mc, S.conf.p, S.log_psi.p, S.angles.p, acc_rej_dev);
+        k_mc_rbm<K, WORDS, true><<<grid, wpb * 32, 0, stream()>>>(d, Wp, mc, S.conf.p, S.log_psi.p, S.angles.p, acc_rej_dev);
     else
-        k_mc_rbm<K, false><<<grid, wpb * 32, 0, stream()>>>(d, mc, S.conf.p, S.log_psi.p, S.angles.p, acc_rej_dev);
+        k_mc_rbm<K, WORDS, false><<<grid, wpb * 32, 0, stream()>>>(d, Wp, mc, S.conf.p, S.log_psi.p, S.angles.p, acc_rej_dev);
     ANGPU_CHECK_LAUNCH(); count_launch();
 }
+template<int K>
+static void launch_mc_rbm_k(const RbmDev& d, const cplx* Wp, const McParams& mc, SampleSet& S, unsigned long long* a) {
+    switch(d.words) {
+        case 1: launch_mc_rbm<K, 1>(d, Wp, mc, S, a); break;
+        case 2: launch_mc_rbm<K, 2>(d, Wp, mc, S, a); break;
+        case 3: launch_mc_rbm<K, 3>(d, Wp, mc, S, a); break;
+        default: launch_mc_rbm<K, 4>(d, Wp, mc, S, a); break;
+    }
+}
+static unsigned rbm_sampler_K(unsigned M) { return M <= 32u ? 1u : M <= 64u ? 2u : M <= 128u ? 4u : M <= 256u ? 8u : 16u; }
+
 void PsiRBM::mc_sample(const McParams& mc, SampleSet& S, unsigned long long* acc_rej_dev) {
     if(mc.num_chains_local == 0) return;
     const RbmDev d = dev();
     if(M <= 512u) {
         S.angles.resize(S.ns * M);
-        if(M <= 32u) launch_mc_rbm<1>(d, mc, S, acc_rej_dev);
-        else if(M <= 64u) launch_mc_rbm<2>(d, mc, S, acc_rej_dev);
-        else if(M <= 128u) launch_mc_rbm<4>(d, mc, S, acc_rej_dev);
-        else if(M <= 256u) launch_mc_rbm<8>(d, mc, S, acc_rej_dev);
-        else launch_mc_rbm<16>(d, mc, S, acc_rej_dev);
+        switch(rbm_sampler_K(M)) {
+            case 1: launch_mc_rbm_k<1>(d, dWpad.p, mc, S, acc_rej_dev); break;
+            case 2: launch_mc_rbm_k<2>(d, dWpad.p, mc, S, acc_rej_dev); break;
+            case 4: launch_mc_rbm_k<4>(d, dWpad.p, mc, S, acc_rej_dev); break;
+            case 8: launch_mc_rbm_k<8>(d, dWpad.p, mc, S, acc_rej_dev); break;
+            default: launch_mc_rbm_k<16>(d, dWpad.p, mc, S, acc_rej_dev); break;
+        }
         S.has_angles = true;
     } else {
         generic_mc(d, mc, S, acc_rej_dev);

@@ -54,7 +54,7 @@ struct PsiRBM : Psi {
     unsigned M = 0;
     cplx fw{1.0, 0.0};
     std::vector<cplx> hW;
-    DevBuf<cplx> dW, dWt;
+    DevBuf<cplx> dW, dWt, dWpad;
 
     PsiRBM(unsigned N_, unsigned M_, const cplx* W, cplx fw_, cplx lp_);
     RbmDev dev() const { return RbmDev{N, M, words, P, lp, fw, dW.p, dWt.p}; }

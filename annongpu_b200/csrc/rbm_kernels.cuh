@@ -68,99 +68,159 @@ __device__ __forceinline__ double lc0_re(cplx z) {
     return fma(1.0 / 45.0, x6, fma(-1.0 / 12.0, x4, 0.5 * x2));
 }
 
-template<int K, bool FW_REAL>
-__global__ void __launch_bounds__(128)
-k_mc_rbm(const RbmDev psi, const McParams mc, uint64_t* __restrict__ conf_out, cplx* __restrict__ log_psi_out,
-         cplx* __restrict__ angles_out, unsigned long long* __restrict__ acc_rej) {
+// 2 warps per block; for K <= 8 (M <= 256, the C2 shape) 9 blocks = 18 warps per SM are requested (<= 112 registers)
+constexpr int MC_RBM_THREADS = 64;
+#ifndef MC_RBM_MINB
+#define MC_RBM_MINB 8
+#endif
+
+// Re / Im of lc0(z) in the variables p = Re z^2 = x^2 - y^2, q = x y (Im z^2 = 2 q):
+//   Re lc0 = p (1/2 - p/12 + p^2/45) + q^2 (1/3 - 12 p/45)          9 DP instructions from (x, y)
+//   Im lc0 = q (1 - p/3 + 2 p^2/15 - 8 q^2/45)
+// (same polynomial as lc0(); fewer operations for the sampler's inner loop, rounding differs at the 1e-16 level)
+__device__ __forceinline__ double lc0_re_pq(double x, double y) {
+    const double p = fma(x, x, -(y * y)), q = x * y, q2 = q * q;
+    double A = fma(p, 1.0 / 45.0, -1.0 / 12.0);
+    A = fma(A, p, 0.5);
+    const double B = fma(p, -12.0 / 45.0, 1.0 / 3.0);
+    return fma(q2, B, A * p);
+}
+__device__ __forceinline__ cplx lc0_pq(double x, double y) {
+    const double p = fma(x, x, -(y * y)), q = x * y, q2 = q * q;
+    double A = fma(p, 1.0 / 45.0, -1.0 / 12.0);
+    A = fma(A, p, 0.5);
+    const double B = fma(p, -12.0 / 45.0, 1.0 / 3.0);
+    double C = fma(p, 2.0 / 15.0, -1.0 / 3.0);
+    C = fma(C, p, 1.0);
+    C = fma(q2, -8.0 / 45.0, C);
+    return cplx(fma(q2, B, A * p), q * C);
+}
+
+// Metropolis acceptance "ratio > 1 || u <= ratio", ratio = exp(d2) (include/ensembles/MonteCarlo.hpp:158-160), decided
+// without a double-precision exp in all but ~1e-4 of the proposals: an fp32 exp screens the comparison and only
+// the band where fp32 cannot decide falls back to the exact evaluation, so the decision is ALWAYS the fp64 one.
+__device__ __forceinline__ bool metropolis_accept(double d2, double u) {
+    if(d2 >= 0.0) return true;
+    const float rf = __expf((float)d2), uf = (float)u;
+    const float band = rf * 1e-4f + 1e-37f;
+    if(uf < rf - band) return true;
+    if(uf > rf + band) return false;
+    return u <= exp(d2);
+}
+
+// spin / flip on a register-resident configuration of a compile-time number of words
+template<int WORDS>
+__device__ __forceinline__ double conf_spin_t(const uint64_t (&c)[MAXW], unsigned site) {
+    if(WORDS == 1) return ((c[0] >> site) & 1ull) ? 1.0 : -1.0;
+    return conf_spin(c, site);
+}
+template<int WORDS>
+__device__ __forceinline__ void conf_flip_t(uint64_t (&c)[MAXW], unsigned site) {
+    if(WORDS == 1) c[0] ^= 1ull << site;
+    else conf_flip(c, site);
+}
+
+// Wp: W with rows padded to Mp = 32*K complex (zeros beyond M) so that the hot loop has no bounds checks and one
+// base address per proposal: lane l reads Wp[site][l + 32k], k < K (coalesced 512 B per k).
+template<int K, int WORDS, bool FW_REAL>
+__global__ void __launch_bounds__(MC_RBM_THREADS, (K <= 8) ? MC_RBM_MINB : 1)
+k_mc_rbm(const RbmDev psi, const cplx* __restrict__ Wp, const McParams mc, uint64_t* __restrict__ conf_out,
+         cplx* __restrict__ log_psi_out, cplx* __restrict__ angles_out, unsigned long long* __restrict__ acc_rej) {
+    constexpr unsigned Mp = 32u * K;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned chain = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if(chain >= mc.num_chains_local) return;
     const unsigned gchain = mc.chain0 + chain;
     const unsigned M = psi.M, N = psi.N;
-    const cplx* __restrict__ W = psi.W;
+    const unsigned tag_init = (mc.call << 1) | 0u, tag_step = (mc.call << 1) | 1u;
+    const cplx* __restrict__ Wl = Wp + lane;
 
     uint32_t r[4];
     uint64_t conf[MAXW] = {0ull, 0ull, 0ull, 0ull};
     #pragma unroll
-    for(unsigned w = 0; w < (unsigned)MAXW; w++) {
-        if(w < psi.words) {
-            philox4x32_10(w, 0u, gchain, (mc.call << 1) | 0u, mc.seed_lo, mc.seed_hi, r);
-            conf[w] = (uint64_t)r[0] | ((uint64_t)r[1] << 32);
-            if(w == psi.words - 1u && (N & 63u)) conf[w] &= (1ull << (N & 63u)) - 1ull;
-        }
+    for(int w = 0; w < WORDS; w++) {
+        philox4x32_10((uint32_t)w, 0u, gchain, tag_init, mc.seed_lo, mc.seed_hi, r);
+        conf[w] = (uint64_t)r[0] | ((uint64_t)r[1] << 32);
     }
+    if(N & 63u) conf[WORDS - 1] &= (1ull << (N & 63u)) - 1ull;
+    // (the host dispatches WORDS == words_for(N), so the last word is the one to mask)
 
+    // units beyond M hold theta = 0 (Wp is zero-padded), for which lc0 = 0
     cplx th[K];
     #pragma unroll
     for(int k = 0; k < K; k++) th[k] = cplx(0.0, 0.0);
     for(unsigned i = 0; i < N; i++) {
-        const double s = conf_spin(conf, i);
+        const double s = conf_spin_t<WORDS>(conf, i);
         #pragma unroll
-        for(int k = 0; k < K; k++) {
-            const unsigned j = lane + 32u * k;
-            if(j < M) th[k] += s * ldg(&W[i * M + j]);
-        }
+        for(int k = 0; k < K; k++) th[k] += s * ldg(&Wl[(size_t)i * Mp + 32u * k]);
     }
-    // current value of Re log psi (only its changes matter for the Metropolis ratio)
-    auto re_log_psi = [&](const cplx (&a)[K]) -> double {
+    auto re_log_psi = [&]() -> double {
         if(FW_REAL) {
             double p = 0.0;
             #pragma unroll
-            for(int k = 0; k < K; k++) if(lane + 32u * k < M) p += lc0_re(a[k]);
+            for(int k = 0; k < K; k++) p += lc0_re_pq(th[k].re, th[k].im);
             return fma(psi.fw.re, warp_sum(p), psi.lp.re);
         } else {
             cplx p(0.0, 0.0);
             #pragma unroll
-            for(int k = 0; k < K; k++) if(lane + 32u * k < M) p += lc0(a[k]);
+            for(int k = 0; k < K; k++) p += lc0_pq(th[k].re, th[k].im);
             p = warp_sum(p);
             return psi.lp.re + psi.fw.re * p.re - psi.fw.im * p.im;
         }
     };
-    double cur_re = re_log_psi(th);
+    double cur_re = re_log_psi();
 
-    unsigned long long t = 0, acc = 0, rej = 0;
     const unsigned therm = mc.num_therm * N, per_sample = mc.num_sweeps * N;
-    for(unsigned s = 0; s <= mc.steps_per_chain; s++) {
-        const unsigned nsteps = (s == 0) ? therm : per_sample;
-        for(unsigned i = 0; i < nsteps; i++, t++) {
-            philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), gchain, (mc.call << 1) | 1u, mc.seed_lo, mc.seed_hi, r);
-            const unsigned site = r[0] % N;
-            const double delta = -2.0 * conf_spin(conf, site);       // s'_p - s_p
-            const cplx* __restrict__ row = W + (size_t)site * M;
-            cplx nth[K];
+    const unsigned long long total_steps = (unsigned long long)therm + (unsigned long long)per_sample * mc.steps_per_chain;
+    unsigned long long acc = 0;
+    unsigned long long next_record = (unsigned long long)therm + per_sample;
+    unsigned sample = 0;
+
+    for(unsigned long long t0 = 0; t0 < total_steps; t0 += 32u) {
+        // one Philox block per lane: lane l draws the random numbers of proposal t0 + l (amortises the generator 32x)
+        philox4x32_10((uint32_t)(t0 + lane), (uint32_t)((t0 + lane) >> 32), gchain, tag_step, mc.seed_lo, mc.seed_hi, r);
+        const unsigned my_site = r[0] % N;
+        const unsigned my_ulo = r[1], my_uhi = r[2];
+        const unsigned nb = (unsigned)min((unsigned long long)32u, total_steps - t0);
+        for(unsigned b = 0; b < nb; b++) {
+            const unsigned site = __shfl_sync(FULL, my_site, b);
+            const cplx* __restrict__ row = Wl + (size_t)site * Mp;
+            cplx w[K];
             #pragma unroll
-            for(int k = 0; k < K; k++) {
-                const unsigned j = lane + 32u * k;
-                nth[k] = th[k];
-                if(j < M) { const cplx w = ldg(&row[j]); nth[k].re = fma(delta, w.re, th[k].re); nth[k].im = fma(delta, w.im, th[k].im); }
-            }
-            const double new_re = re_log_psi(nth);
-            const double ratio = exp(2.0 * (new_re - cur_re));
-            const double u = u01_from_bits(r[1], r[2]);
-            if(ratio > 1.0 || u <= ratio) {
-                #pragma unroll
-                for(int k = 0; k < K; k++) th[k] = nth[k];
+            for(int k = 0; k < K; k++) w[k] = ldg(&row[32u * k]);
+            const double u = u01_from_bits(__shfl_sync(FULL, my_ulo, b), __shfl_sync(FULL, my_uhi, b));
+            const double delta = -2.0 * conf_spin_t<WORDS>(conf, site);           // s'_p - s_p
+            #pragma unroll
+            for(int k = 0; k < K; k++) { th[k].re = fma(delta, w[k].re, th[k].re); th[k].im = fma(delta, w[k].im, th[k].im); }
+            const double new_re = re_log_psi();
+            if(metropolis_accept(2.0 * (new_re - cur_re), u)) {
                 cur_re = new_re;
-                conf_flip(conf, site);
+                conf_flip_t<WORDS>(conf, site);
                 acc++;
-            } else rej++;
-        }
-        if(s == 0) continue;
-        const size_t idx = (size_t)(s - 1u) * mc.num_chains_local + chain;
-        cplx p(0.0, 0.0);
-        #pragma unroll
-        for(int k = 0; k < K; k++) {
-            const unsigned j = lane + 32u * k;
-            if(j < M) { p += lc0(th[k]); if(angles_out) angles_out[idx * M + j] = th[k]; }
-        }
-        p = warp_sum(p);
-        if(lane == 0) {
-            log_psi_out[idx] = psi.lp + psi.fw * p;
-            #pragma unroll
-            for(unsigned w = 0; w < (unsigned)MAXW; w++) if(w < psi.words) conf_out[idx * psi.words + w] = conf[w];
+            } else {
+                // undo, as the reference does on rejection (update_input_units(next -> current), MonteCarlo.hpp:173-175)
+                #pragma unroll
+                for(int k = 0; k < K; k++) { th[k].re = fma(-delta, w[k].re, th[k].re); th[k].im = fma(-delta, w[k].im, th[k].im); }
+            }
+            if(t0 + b + 1u == next_record) {
+                const size_t idx = (size_t)sample * mc.num_chains_local + chain;
+                cplx p(0.0, 0.0);
+                #pragma unroll
+                for(int k = 0; k < K; k++) {
+                    const unsigned j = lane + 32u * k;
+                    if(j < M) { p += lc0(th[k]); if(angles_out) angles_out[idx * M + j] = th[k]; }
+                }
+                p = warp_sum(p);
+                if(lane == 0) {
+                    log_psi_out[idx] = psi.lp + psi.fw * p;
+                    #pragma unroll
+                    for(int ww = 0; ww < WORDS; ww++) conf_out[idx * WORDS + ww] = conf[ww];
+                }
+                sample++; next_record += per_sample;
+            }
         }
     }
-    if(lane == 0) { atomicAdd(&acc_rej[0], acc); atomicAdd(&acc_rej[1], rej); }
+    if(lane == 0) { atomicAdd(&acc_rej[0], acc); atomicAdd(&acc_rej[1], total_steps - acc); }
 }
 
 // theta = W^T s and log psi for given configurations (ExactSummation / probes); one warp per configuration.
@@ -188,12 +248,18 @@ __global__ void k_rbm_angles(const RbmDev psi, const uint64_t* __restrict__ conf
 }
 
 constexpr int RBM_ELOC_MAXF = 4;   // flips per group handled by the fast path (Heisenberg/TFIM: <= 2)
+constexpr int RBM_ELOC_SPLIT = 4;  // lanes per flip group: each takes the hidden units j = p (mod 4)
 
 // smem per warp: theta[M] cplx | list_C[num_groups] cplx | list_g[num_groups] unsigned (padded to 16 B)
 __host__ __device__ inline size_t rbm_eloc_slice_bytes(unsigned M, unsigned num_groups) {
     return (size_t)M * sizeof(cplx) + (size_t)num_groups * sizeof(cplx) + (((size_t)num_groups * sizeof(unsigned) + 15u) & ~(size_t)15u);
 }
 
+// One warp per sample.  Work item = (active flip group, quarter of the hidden units); 32 items per pass, so a sample
+// with `a` active groups needs ceil(a/8) passes of M/4 units each (a = #antiparallel bonds ~ N/2 for the Heisenberg ring).
+// theta_j is read from shared memory (4 consecutive complex per quad: conflict-free), W^T[j][site] from L1/L2
+// (8 consecutive sites x 4 rows per instruction); NF = max flips per group (compile time, unused slots have delta = 0).
+template<int NF>
 __global__ void __launch_bounds__(256)
 k_eloc_rbm(const RbmDev psi, const OpDev op, const uint64_t* __restrict__ confs, const cplx* __restrict__ angles,
            size_t ns, cplx* __restrict__ eloc_out) {
@@ -205,12 +271,13 @@ k_eloc_rbm(const RbmDev psi, const OpDev op, const uint64_t* __restrict__ confs,
     cplx* list_C = theta + M;
     unsigned* list_g = reinterpret_cast<unsigned*>(list_C + G);
     const cplx* __restrict__ Wt = psi.Wt;
+    const unsigned part = lane & (RBM_ELOC_SPLIT - 1), slot = lane / RBM_ELOC_SPLIT;   // 8 groups per pass
 
     for(size_t s = (size_t)blockIdx.x * wpb + (threadIdx.x >> 5); s < ns; s += (size_t)gridDim.x * wpb) {
         uint64_t conf[MAXW];
         conf_load(conf, confs + s * psi.words, psi.words);
         cplx basep(0.0, 0.0);
-        for(unsigned j = lane; j < M; j += 32u) { const cplx a = angles[s * M + j]; theta[j] = a; basep += lc0(a); }
+        for(unsigned j = lane; j < M; j += 32u) { const cplx a = angles[s * M + j]; theta[j] = a; basep += lc0_pq(a.re, a.im); }
         const cplx base_sum = warp_sum(basep);
 
         // diagonal strings + per-group coefficients, compacted
@@ -231,36 +298,42 @@ k_eloc_rbm(const RbmDev psi, const OpDev op, const uint64_t* __restrict__ confs,
         }
         __syncwarp();
 
-        for(unsigned idx0 = 0; idx0 < count; idx0 += 32u) {
-            const unsigned idx = idx0 + lane;
-            if(idx < count) {
+        for(unsigned idx0 = 0; idx0 < count; idx0 += 32u / RBM_ELOC_SPLIT) {
+            const unsigned idx = idx0 + slot;
+            const bool valid = idx < count;
+            unsigned site[NF]; double dl[NF];
+            #pragma unroll
+            for(int f = 0; f < NF; f++) { site[f] = 0u; dl[f] = 0.0; }
+            if(valid) {
                 const unsigned g = list_g[idx];
-                unsigned site[RBM_ELOC_MAXF]; double dl[RBM_ELOC_MAXF];
                 int nf = 0;
-                #pragma unroll
-                for(int f = 0; f < RBM_ELOC_MAXF; f++) { site[f] = 0u; dl[f] = 0.0; }
                 for(unsigned w = 0; w < op.words; w++) {
                     uint64_t m = op.flip[g * op.words + w];
                     while(m) {
                         const unsigned p = w * 64u + (unsigned)__ffsll((long long)m) - 1u;
                         #pragma unroll
-                        for(int f = 0; f < RBM_ELOC_MAXF; f++) if(f == nf) { site[f] = p; dl[f] = -2.0 * conf_spin(conf, p); }
+                        for(int f = 0; f < NF; f++) if(f == nf) { site[f] = p; dl[f] = -2.0 * conf_spin(conf, p); }
                         nf++;
                         m &= m - 1ull;
                     }
                 }
-                cplx acc(0.0, 0.0);
-                for(unsigned j = 0; j < M; j++) {
-                    cplx a = theta[j];
-                    const cplx* __restrict__ wr = Wt + (size_t)j * N;
-                    #pragma unroll
-                    for(int f = 0; f < RBM_ELOC_MAXF; f++) {
-                        if(f < nf) { const cplx w = ldg(&wr[site[f]]); a.re = fma(dl[f], w.re, a.re); a.im = fma(dl[f], w.im, a.im); }
-                    }
-                    acc += lc0(a);
-                }
-                E += list_C[idx] * cexp(psi.fw * (acc - base_sum));
             }
+            cplx acc(0.0, 0.0);
+            #pragma unroll 4
+            for(unsigned j = part; j < M; j += RBM_ELOC_SPLIT) {
+                cplx a = theta[j];
+                const cplx* __restrict__ wr = Wt + (size_t)j * N;
+                #pragma unroll
+                for(int f = 0; f < NF; f++) { const cplx w = ldg(&wr[site[f]]); a.re = fma(dl[f], w.re, a.re); a.im = fma(dl[f], w.im, a.im); }
+                acc += lc0_pq(a.re, a.im);
+            }
+            // combine the 4 quarters of each group
+            #pragma unroll
+            for(int o = 1; o < RBM_ELOC_SPLIT; o <<= 1) {
+                acc.re += __shfl_xor_sync(FULL, acc.re, o);
+                acc.im += __shfl_xor_sync(FULL, acc.im, o);
+            }
+            if(valid && part == 0) E += list_C[idx] * cexp(psi.fw * (acc - base_sum));
         }
         E = warp_sum(E);
         if(lane == 0) eloc_out[s] = E;

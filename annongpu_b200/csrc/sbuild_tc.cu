@@ -1,0 +1,321 @@
+// S-matrix build on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a only.
+//
+//   S_rc = sum_s conj(A_sr) A_sc,   A_sk = sqrt(w_s) (O_sk - <O_k>)        (TDVP.cu.template:216-302, centred form)
+//        = [Re_r.Re_c + Im_r.Im_c] + i [Re_r.Im_c - Im_r.Re_c]            (dot products over the samples)
+//
+// The reference builds S with ns*P^2 global fp64 atomics (TDVP.cu.template:260-263).  Here the one genuinely dense
+// contraction of the path runs as a TF32 tensor-core GEMM with fp32 accumulation in TMEM, made ~fp32-accurate by the
+// standard 3xTF32 split  x = hi + lo (both TF32-exact):  a.b ~= hi.hi + hi.lo + lo.hi.   Centring and sqrt(w) scaling are
+// applied in fp64 BEFORE the split, so no large mean term is cancelled in reduced precision.
+// This is the opt-in FAST path (tolerance ~1e-5 relative to ||S||, BASELINE.json's fp32 tolerance); the default
+// TDVP::build_S (vmc.cu: k_zherk) stays exact fp64.
+//
+// Data:   k_pack_planes  transposes O [ns][P] (complex fp64) into four K-major fp32 planes [P][Kpad]:
+//         Re_hi, Re_lo, Im_hi, Im_lo (row = parameter, contiguous over samples, zero padded to Kpad).
+// Kernel: k_sbuild_tf32  one CTA per upper-triangular 128x128 tile pair (tr <= tc), 192 threads:
+//           warp 0      TMA producer   8 tiles / stage: {Re,Im} x {hi,lo} for the row block and the column block
+//                                      (box 16 fp32 x 128 rows, 64B swizzle), 3 stages x 64 KB
+//           warp 1      MMA issuer     12 x (BLOCK_K/8) tcgen05.mma.kind::tf32 per stage into two 128x128 fp32
+//                                      accumulators in TMEM (Re S, Im S; Im uses the negate-A bit), tcgen05.commit -> mbarrier
+//           warps 2-5   epilogue       tcgen05.ld 32x32b -> fp64 -> S[r][c] and its Hermitian mirror S[c][r]
+#include "vmc.hpp"
+#include <cuda.h>
+#include <cmath>
+
+namespace angpu {
+
+namespace tc {
+
+constexpr int BLOCK_MN = 128;       // output tile (parameters x parameters)
+constexpr int BLOCK_K = 16;         // samples per stage: 16 fp32 = 64 B rows (SWIZZLE_64B)
+constexpr int UMMA_K = 8;           // tf32: 32 bytes per MMA
+constexpr int STAGES = 3;
+constexpr int TILE_BYTES = BLOCK_MN * BLOCK_K * 4;            // 8 KB
+constexpr int TILES_PER_STAGE = 8;
+constexpr int STAGE_BYTES = TILES_PER_STAGE * TILE_BYTES;     // 64 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int TMEM_COLS = 256;      // two 128-column fp32 accumulators
+constexpr int THREADS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while(!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+// shared-memory matrix descriptor, K-major operand, 64-byte swizzle: 8-row groups are 512 B apart (SBO), LBO unused
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);            // start address
+    d |= (uint64_t)0 << 16;                                   // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(512u >> 4) << 32;                         // stride byte offset
+    d |= (uint64_t)1 << 46;                                   // descriptor version (sm_100)
+    d |= (uint64_t)4 << 61;                                   // layout type: SWIZZLE_64B
+    return d;
+}
+// instruction descriptor, kind::tf32, fp32 accumulate, K-major A and B, M = N = 128
+__device__ __forceinline__ uint32_t umma_idesc_tf32(bool negate_a) {
+    uint32_t d = 0;
+    d |= 1u << 4;                            // D format: F32
+    d |= 2u << 7;                            // A format: TF32
+    d |= 2u << 10;                           // B format: TF32
+    d |= (negate_a ? 1u : 0u) << 13;         // negate A
+    d |= (uint32_t)(BLOCK_MN >> 3) << 17;    // N
+    d |= (uint32_t)(BLOCK_MN >> 4) << 24;    // M
+    return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr) : "memory");
+}
+
+struct Maps { CUtensorMap re_hi, re_lo, im_hi, im_lo; };
+
+__global__ void __launch_bounds__(THREADS, 1)
+k_sbuild_tf32(const __grid_constant__ Maps maps, unsigned P, unsigned num_kb, cplx* __restrict__ S) {
+    extern __shared__ unsigned char smem_raw[];
+    // 1024-byte aligned tile area, then the barriers
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t tiles = (raw + 1023u) & ~1023u;
+    const uint32_t bars = tiles + STAGES * STAGE_BYTES;          // full[STAGES], empty[STAGES], tmem_full, tmem_ptr
+    const uint32_t bar_full = bars, bar_empty = bars + 8u * STAGES, bar_tmem = bars + 16u * STAGES, tmem_slot = bar_tmem + 8u;
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+
+    // upper-triangular tile pair
+    const unsigned nt = (P + BLOCK_MN - 1) / BLOCK_MN;
+    unsigned t = blockIdx.x, tr = 0;
+    while(t >= nt - tr) { t -= nt - tr; tr++; }
+    const unsigned tc_ = tr + t;
+    const int row0 = (int)(tr * BLOCK_MN), col0 = (int)(tc_ * BLOCK_MN);
+
+    if(threadIdx.x == 0) {
+        for(int s = 0; s < STAGES; s++) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, 1); }
+        mbar_init(bar_tmem, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if(warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+    if(warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if(lane == 0) {
+            const CUtensorMap* m[4] = {&maps.re_hi, &maps.re_lo, &maps.im_hi, &maps.im_lo};
+            for(unsigned kb = 0; kb < num_kb; kb++) {
+                const unsigned s = kb % STAGES, ph = (kb / STAGES) & 1u;
+                mbar_wait(bar_empty + 8u * s, ph ^ 1u);
+                mbar_arrive_expect_tx(bar_full + 8u * s, (uint32_t)STAGE_BYTES);
+                const uint32_t base = tiles + s * STAGE_BYTES;
+                const int k0 = (int)(kb * BLOCK_K);
+                #pragma unroll
+                for(int q = 0; q < 4; q++) {
+                    tma_load_2d(base + (uint32_t)q * TILE_BYTES, m[q], k0, row0, bar_full + 8u * s);         // row block planes
+                    tma_load_2d(base + (uint32_t)(4 + q) * TILE_BYTES, m[q], k0, col0, bar_full + 8u * s);   // column block planes
+                }
+            }
+        }
+    } else if(warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if(lane == 0) {
+            const uint32_t id_pos = umma_idesc_tf32(false), id_neg = umma_idesc_tf32(true);
+            const uint32_t acc_re = tmem_base, acc_im = tmem_base + (uint32_t)BLOCK_MN;
+            for(unsigned kb = 0; kb < num_kb; kb++) {
+                const unsigned s = kb % STAGES, ph = (kb / STAGES) & 1u;
+                mbar_wait(bar_full + 8u * s, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t base = tiles + s * STAGE_BYTES;
+                // tile order in a stage: 0 Re_r_hi, 1 Re_r_lo, 2 Im_r_hi, 3 Im_r_lo, 4 Re_c_hi, 5 Re_c_lo, 6 Im_c_hi, 7 Im_c_lo
+                #pragma unroll
+                for(int k = 0; k < BLOCK_K / UMMA_K; k++) {
+                    const uint32_t koff = (uint32_t)(k * UMMA_K * 4);
+                    uint64_t d[8];
+                    #pragma unroll
+                    for(int q = 0; q < 8; q++) d[q] = umma_desc_sw64(base + (uint32_t)q * TILE_BYTES + koff);
+                    const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
+                    // Re S += Re_r.Re_c + Im_r.Im_c      (hi.hi + hi.lo + lo.hi each)
+                    umma_tf32(acc_re, d[0], d[4], id_pos, first);
+                    umma_tf32(acc_re, d[0], d[5], id_pos, 1u);
+                    umma_tf32(acc_re, d[1], d[4], id_pos, 1u);
+                    umma_tf32(acc_re, d[2], d[6], id_pos, 1u);
+                    umma_tf32(acc_re, d[2], d[7], id_pos, 1u);
+                    umma_tf32(acc_re, d[3], d[6], id_pos, 1u);
+                    // Im S += Re_r.Im_c - Im_r.Re_c
+                    umma_tf32(acc_im, d[0], d[6], id_pos, first);
+                    umma_tf32(acc_im, d[0], d[7], id_pos, 1u);
+                    umma_tf32(acc_im, d[1], d[6], id_pos, 1u);
+                    umma_tf32(acc_im, d[2], d[4], id_neg, 1u);
+                    umma_tf32(acc_im, d[2], d[5], id_neg, 1u);
+                    umma_tf32(acc_im, d[3], d[4], id_neg, 1u);
+                }
+                umma_commit(bar_empty + 8u * s);            // frees the stage when these MMAs have read it
+            }
+            umma_commit(bar_tmem);                          // accumulators complete
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        const unsigned quarter = warp & 3u;                 // TMEM lane quarter this warp may access
+        mbar_wait(bar_tmem, 0u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const unsigned m_local = quarter * 32u + lane;
+        const unsigned r = (unsigned)row0 + m_local;
+        #pragma unroll 1
+        for(int c16 = 0; c16 < BLOCK_MN / 16; c16++) {
+            uint32_t vre[16], vim[16];
+            const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + (uint32_t)(c16 * 16);
+            tmem_ld16(taddr, vre);
+            tmem_ld16(taddr + (uint32_t)BLOCK_MN, vim);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if(r < P) {
+                #pragma unroll
+                for(int j = 0; j < 16; j++) {
+                    const unsigned c = (unsigned)col0 + (unsigned)(c16 * 16 + j);
+                    if(c < P) {
+                        const cplx v((double)__uint_as_float(vre[j]), (double)__uint_as_float(vim[j]));
+                        if(tr != tc_) { S[(size_t)r * P + c] = v; S[(size_t)c * P + r] = conj(v); }
+                        else if(c >= r) { S[(size_t)r * P + c] = v; if(c != r) S[(size_t)c * P + r] = conj(v); }
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if(warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+}
+
+// O [ns][P] complex fp64 -> planes [P][Kpad] fp32: A = sqrt(w) (O - Obar), split hi/lo in TF32. 32x32 smem transpose.
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__global__ void __launch_bounds__(256) k_pack_planes(const cplx* __restrict__ O, const double* __restrict__ w, const cplx* __restrict__ Obar,
+                                                     double inv_W, size_t ns, unsigned P, size_t Kpad, float* __restrict__ re_hi, float* __restrict__ re_lo,
+                                                     float* __restrict__ im_hi, float* __restrict__ im_lo) {
+    __shared__ double tre[32][33], tim[32][33];
+    const unsigned tx = threadIdx.x & 31u, ty = threadIdx.x >> 5;      // 32 x 8
+    const size_t s0 = (size_t)blockIdx.y * 32u;
+    const unsigned k0 = blockIdx.x * 32u;
+    for(unsigned j = ty; j < 32u; j += 8u) {
+        const size_t s = s0 + j; const unsigned k = k0 + tx;
+        double a = 0.0, b = 0.0;
+        if(s < ns && k < P) {
+            const double sw = sqrt(w[s]);
+            const cplx o = O[s * P + k], m = inv_W * Obar[k];
+            a = sw * (o.re - m.re); b = sw * (o.im - m.im);
+        }
+        tre[j][tx] = a; tim[j][tx] = b;
+    }
+    __syncthreads();
+    for(unsigned j = ty; j < 32u; j += 8u) {
+        const unsigned k = k0 + j; const size_t s = s0 + tx;
+        if(k < P && s < Kpad) {
+            const double a = tre[tx][j], b = tim[tx][j];
+            const float ah = to_tf32((float)a), bh = to_tf32((float)b);
+            const float al = to_tf32((float)(a - (double)ah)), bl = to_tf32((float)(b - (double)bh));
+            const size_t idx = (size_t)k * Kpad + s;
+            re_hi[idx] = ah; re_lo[idx] = al; im_hi[idx] = bh; im_lo[idx] = bl;
+        }
+    }
+}
+
+// S_rc += corr * conj(Obar_r) Obar_c  — restores the reference's un-normalised-weights convention
+// S = sum w O*O - <O>*<O> when W = sum w != 1 (centring with <O>/W gives sum w O*O - <O>*<O>/W)
+__global__ void k_rank1_add(cplx* __restrict__ S, const cplx* __restrict__ Obar, double corr, unsigned P) {
+    const size_t total = (size_t)P * P;
+    for(size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = e / P, c = e % P;
+        S[e] += corr * (conj(Obar[r]) * Obar[c]);
+    }
+}
+
+typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static encode_fn get_encode() {
+    static encode_fn fn = nullptr;
+    if(!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        ANGPU_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        ANGPU_REQUIRE(p != nullptr && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available in this driver");
+        fn = reinterpret_cast<encode_fn>(p);
+    }
+    return fn;
+}
+static void make_map(CUtensorMap* m, float* plane, unsigned P, size_t Kpad) {
+    const cuuint64_t gdim[2] = {(cuuint64_t)Kpad, (cuuint64_t)P};
+    const cuuint64_t gstride[1] = {(cuuint64_t)Kpad * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)BLOCK_MN};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, plane, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if(r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+}
+
+} // namespace tc
+
+// S = (1/1) sum_s conj(A_sr) A_sc on the tensor cores.  Single-process only in this round (the centred form needs the
+// global <O_k>, which eval() has already all-reduced; the partial S of each rank is all-reduced afterwards).
+void TDVP::build_S_tensorcore() {
+    ANGPU_REQUIRE(evaluated, "TDVP: call eval first");
+    ensure_dense_O(last_psi);
+    mark(5);
+    const size_t ns = S.ns;
+    const size_t Kpad = std::max<size_t>(tc::BLOCK_K, (ns + tc::BLOCK_K - 1) / tc::BLOCK_K * tc::BLOCK_K);
+    Smat.resize((size_t)P * P);
+    tc_planes.resize((size_t)4 * P * Kpad);
+    float* re_hi = tc_planes.p; float* re_lo = re_hi + (size_t)P * Kpad; float* im_hi = re_lo + (size_t)P * Kpad; float* im_lo = im_hi + (size_t)P * Kpad;
+    const double W = total_weight > 0.0 ? total_weight : 1.0;
+    tc::k_pack_planes<<<dim3(ceil_div(P, 32), ceil_div(Kpad, 32)), 256, 0, stream()>>>(O.p, S.weight.p, Ok_dev(), 1.0 / W, ns, P, Kpad, re_hi, re_lo, im_hi, im_lo);
+    ANGPU_CHECK_LAUNCH(); count_launch();
+    tc::Maps maps;
+    tc::make_map(&maps.re_hi, re_hi, P, Kpad); tc::make_map(&maps.re_lo, re_lo, P, Kpad);
+    tc::make_map(&maps.im_hi, im_hi, P, Kpad); tc::make_map(&maps.im_lo, im_lo, P, Kpad);
+    const unsigned nt = (P + tc::BLOCK_MN - 1) / tc::BLOCK_MN, tiles = nt * (nt + 1) / 2;
+    ANGPU_CUDA(cudaFuncSetAttribute(tc::k_sbuild_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    tc::k_sbuild_tf32<<<tiles, tc::THREADS, tc::SMEM_BYTES, stream()>>>(maps, P, (unsigned)(Kpad / tc::BLOCK_K), Smat.p);
+    ANGPU_CHECK_LAUNCH(); count_launch();
+    allreduce_sum(reinterpret_cast<double*>(Smat.p), 2 * (size_t)P * P);
+    if(std::fabs(1.0 / W - 1.0) > 1e-14) {
+        const size_t total = (size_t)P * P;
+        tc::k_rank1_add<<<(unsigned)std::min<size_t>((total + 255) / 256, (size_t)ctx().num_sms * 32), 256, 0, stream()>>>(Smat.p, Ok_dev(), 1.0 / W - 1.0, P);
+        ANGPU_CHECK_LAUNCH(); count_launch();
+    }
+    have_S = true;
+    mark(6);
+    if(profile) { ANGPU_CUDA(cudaEventSynchronize(ev[6])); ANGPU_CUDA(cudaEventElapsedTime(&phase_ms[4], ev[5], ev[6])); }
+}
+
+} // namespace angpu

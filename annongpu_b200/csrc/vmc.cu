@@ -9,6 +9,7 @@ namespace angpu {
 static allreduce_fn g_allreduce = nullptr;
 static void* g_allreduce_user = nullptr;
 void set_allreduce(allreduce_fn fn, void* user) { g_allreduce = fn; g_allreduce_user = user; }
+bool has_allreduce() { return g_allreduce != nullptr; }
 void allreduce_sum(double* dev_ptr, size_t count) {
     if(g_allreduce && count) g_allreduce(dev_ptr, (unsigned long long)count, g_allreduce_user);
 }
@@ -98,37 +99,69 @@ __global__ void __launch_bounds__(128) k_col_reduce_dense(const cplx* __restrict
     part_x[(size_t)blockIdx.y * P + k] = x;
 }
 
-// PsiRBM factorised rows O_s,(i,j) = sigma_si T_sj: thread = column j, 8 sites per thread
-constexpr int RBM_IT = 8;
+// PsiRBM factorised rows O_s,(i,j) = sigma_si T_sj.  Thread = column j with RBM_IT sites in registers; the signs of a
+// 32-sample tile are staged in shared memory as +-1.0 doubles (warp-broadcast LDS.128), so the inner loop is
+// 1 LDG (T) + RBM_IT/2 LDS + 2*RBM_IT DFMA per sample (4*RBM_IT with the mean).  Samples are split in chunks
+// (blockIdx.z) whose partial sums are added in fixed order afterwards (deterministic, no atomics).
+constexpr int RBM_IT = 16, RBM_TS = 32;
+template<bool WANT_MEAN>
 __global__ void __launch_bounds__(128) k_col_reduce_rbm(const uint64_t* __restrict__ conf, const cplx* __restrict__ T,
         const double* __restrict__ w, const cplx* __restrict__ X, size_t ns, unsigned N, unsigned M, unsigned words, size_t chunk,
         cplx* __restrict__ part_mean, cplx* __restrict__ part_x) {
+    __shared__ __align__(16) double sgn[RBM_TS][RBM_IT];
+    __shared__ cplx swx[RBM_TS];
+    __shared__ double sw[RBM_TS];
     const unsigned j = blockIdx.x * 128u + threadIdx.x;
     const unsigned i0 = blockIdx.y * RBM_IT;
     const size_t s0 = (size_t)blockIdx.z * chunk, s1 = min(ns, s0 + chunk);
-    if(j >= M) return;
-    cplx m[RBM_IT], x[RBM_IT];
+    const bool jok = j < M;
+    cplx m[WANT_MEAN ? RBM_IT : 1], x[RBM_IT];
     #pragma unroll
-    for(int ii = 0; ii < RBM_IT; ii++) { m[ii] = cplx(0.0, 0.0); x[ii] = cplx(0.0, 0.0); }
-    const unsigned word = i0 >> 6, shift = i0 & 63u;     // RBM_IT divides 64: the 8 sites share one word
-    for(size_t s = s0; s < s1; s++) {
-        const cplx t = T[s * M + j];
-        const double ws = w[s];
-        const cplx a = ws * t, b = (ws * X[s]) * conj(t);
-        const unsigned bits = (unsigned)(conf[s * words + word] >> shift);
-        #pragma unroll
-        for(int ii = 0; ii < RBM_IT; ii++) {
-            const double sg = ((bits >> ii) & 1u) ? 1.0 : -1.0;
-            m[ii].re = fma(sg, a.re, m[ii].re); m[ii].im = fma(sg, a.im, m[ii].im);
-            x[ii].re = fma(sg, b.re, x[ii].re); x[ii].im = fma(sg, b.im, x[ii].im);
+    for(int ii = 0; ii < RBM_IT; ii++) { x[ii] = cplx(0.0, 0.0); if(WANT_MEAN) m[ii] = cplx(0.0, 0.0); }
+    const unsigned word = i0 >> 6, shift = i0 & 63u;     // RBM_IT divides 64: the sites of a tile share one word
+    for(size_t sb = s0; sb < s1; sb += RBM_TS) {
+        __syncthreads();
+        for(unsigned e = threadIdx.x; e < RBM_TS * RBM_IT; e += 128u) {
+            const unsigned st = e / RBM_IT, ii = e % RBM_IT;
+            const size_t s = sb + st;
+            double sg = 0.0;
+            if(s < s1) sg = ((conf[s * words + word] >> (shift + ii)) & 1ull) ? 1.0 : -1.0;
+            sgn[st][ii] = sg;
+        }
+        if(threadIdx.x < RBM_TS) {
+            const size_t s = sb + threadIdx.x;
+            const double ws = (s < s1) ? w[s] : 0.0;
+            sw[threadIdx.x] = ws;
+            swx[threadIdx.x] = (s < s1) ? ws * X[s] : cplx(0.0, 0.0);
+        }
+        __syncthreads();
+        const unsigned nst = (unsigned)min((size_t)RBM_TS, s1 - sb);
+        if(jok) {
+            for(unsigned st = 0; st < nst; st++) {
+                const cplx t = T[(sb + st) * M + j];
+                const cplx b = swx[st] * conj(t);
+                cplx a(0.0, 0.0);
+                if(WANT_MEAN) a = sw[st] * t;
+                #pragma unroll
+                for(int ii = 0; ii < RBM_IT; ii += 2) {
+                    const double2 sg = *reinterpret_cast<const double2*>(&sgn[st][ii]);
+                    x[ii].re = fma(sg.x, b.re, x[ii].re); x[ii].im = fma(sg.x, b.im, x[ii].im);
+                    x[ii + 1].re = fma(sg.y, b.re, x[ii + 1].re); x[ii + 1].im = fma(sg.y, b.im, x[ii + 1].im);
+                    if(WANT_MEAN) {
+                        m[ii].re = fma(sg.x, a.re, m[ii].re); m[ii].im = fma(sg.x, a.im, m[ii].im);
+                        m[ii + 1].re = fma(sg.y, a.re, m[ii + 1].re); m[ii + 1].im = fma(sg.y, a.im, m[ii + 1].im);
+                    }
+                }
+            }
         }
     }
+    if(!jok) return;
     const size_t P = (size_t)N * M;
     #pragma unroll
     for(int ii = 0; ii < RBM_IT; ii++) {
         const unsigned i = i0 + ii;
         if(i < N) {
-            if(part_mean) part_mean[(size_t)blockIdx.z * P + (size_t)i * M + j] = m[ii];
+            if(WANT_MEAN) part_mean[(size_t)blockIdx.z * P + (size_t)i * M + j] = m[ii];
             part_x[(size_t)blockIdx.z * P + (size_t)i * M + j] = x[ii];
         }
     }
@@ -155,47 +188,67 @@ __global__ void __launch_bounds__(256) k_rowdot_dense(const cplx* __restrict__ O
     if(threadIdx.x == 0) { cplx r(0.0, 0.0); for(int i = 0; i < 8; i++) r += sm[i]; a[s] = r; }
 }
 
-// a_s = sum_j T_sj (sum_i sigma_si v_ij)   (PsiRBM factorised rows; block = 8 samples, threads over j)
-constexpr int RBM_ST = 8;
+// a_s = sum_j T_sj (sum_i sigma_si v_ij)   (PsiRBM factorised rows).  Block = 32 samples x all j; thread = 8 samples x 2
+// columns (j, j+64) per 128-column block; signs staged in shared memory as +-1.0 doubles [site][sample] so that the 8
+// samples of a thread are 4 broadcast LDS.128; v is read once per block (L1/L2): ns/32 re-reads instead of ns/8.
+constexpr int RBM_ST = 32, RBM_SI = 64;
 __global__ void __launch_bounds__(256) k_rowdot_rbm(const uint64_t* __restrict__ conf, const cplx* __restrict__ T, const cplx* __restrict__ v,
         size_t ns, unsigned N, unsigned M, unsigned words, cplx* __restrict__ a) {
+    __shared__ __align__(16) double sgn[RBM_SI][RBM_ST];
+    __shared__ cplx red[RBM_ST][2];
     const size_t sb = (size_t)blockIdx.x * RBM_ST;
-    __shared__ uint64_t sconf[RBM_ST][MAXW];
-    __shared__ cplx sm[RBM_ST][8];
-    if(threadIdx.x < RBM_ST * MAXW) {
-        const unsigned st = threadIdx.x / MAXW, wd = threadIdx.x % MAXW;
-        sconf[st][wd] = (sb + st < ns && wd < words) ? conf[(sb + st) * words + wd] : 0ull;
-    }
-    __syncthreads();
-    cplx tot[RBM_ST];
+    const unsigned sg8 = (threadIdx.x >> 6) * 8u, jt = threadIdx.x & 63u;
+    cplx tot[8];
     #pragma unroll
-    for(int st = 0; st < RBM_ST; st++) tot[st] = cplx(0.0, 0.0);
-    for(unsigned j = threadIdx.x; j < M; j += 256u) {
-        cplx inner[RBM_ST];
+    for(int q = 0; q < 8; q++) tot[q] = cplx(0.0, 0.0);
+    for(unsigned jb = 0; jb < M; jb += 128u) {
+        const unsigned j0 = jb + jt, j1 = j0 + 64u;
+        const bool ok0 = j0 < M, ok1 = j1 < M;
+        cplx in0[8], in1[8];
         #pragma unroll
-        for(int st = 0; st < RBM_ST; st++) inner[st] = cplx(0.0, 0.0);
-        for(unsigned i = 0; i < N; i++) {
-            const cplx x = v[(size_t)i * M + j];
-            #pragma unroll
-            for(int st = 0; st < RBM_ST; st++) {
-                const double sg = ((sconf[st][i >> 6] >> (i & 63u)) & 1ull) ? 1.0 : -1.0;
-                inner[st].re = fma(sg, x.re, inner[st].re); inner[st].im = fma(sg, x.im, inner[st].im);
+        for(int q = 0; q < 8; q++) { in0[q] = cplx(0.0, 0.0); in1[q] = cplx(0.0, 0.0); }
+        for(unsigned ib = 0; ib < N; ib += RBM_SI) {
+            __syncthreads();
+            for(unsigned e = threadIdx.x; e < RBM_SI * RBM_ST; e += 256u) {
+                const unsigned ii = e / RBM_ST, st = e % RBM_ST;
+                const unsigned i = ib + ii;
+                double sg = 0.0;
+                if(sb + st < ns && i < N) sg = ((conf[(sb + st) * words + (i >> 6)] >> (i & 63u)) & 1ull) ? 1.0 : -1.0;
+                sgn[ii][st] = sg;
+            }
+            __syncthreads();
+            const unsigned ni = min((unsigned)RBM_SI, N - ib);
+            for(unsigned ii = 0; ii < ni; ii++) {
+                const size_t row = (size_t)(ib + ii) * M;
+                const cplx v0 = ok0 ? v[row + j0] : cplx(0.0, 0.0);
+                const cplx v1 = ok1 ? v[row + j1] : cplx(0.0, 0.0);
+                #pragma unroll
+                for(int q = 0; q < 8; q += 2) {
+                    const double2 sg = *reinterpret_cast<const double2*>(&sgn[ii][sg8 + q]);
+                    in0[q].re = fma(sg.x, v0.re, in0[q].re); in0[q].im = fma(sg.x, v0.im, in0[q].im);
+                    in1[q].re = fma(sg.x, v1.re, in1[q].re); in1[q].im = fma(sg.x, v1.im, in1[q].im);
+                    in0[q + 1].re = fma(sg.y, v0.re, in0[q + 1].re); in0[q + 1].im = fma(sg.y, v0.im, in0[q + 1].im);
+                    in1[q + 1].re = fma(sg.y, v1.re, in1[q + 1].re); in1[q + 1].im = fma(sg.y, v1.im, in1[q + 1].im);
+                }
             }
         }
         #pragma unroll
-        for(int st = 0; st < RBM_ST; st++) if(sb + st < ns) cfma(tot[st], T[(sb + st) * M + j], inner[st]);
+        for(int q = 0; q < 8; q++) {
+            const size_t s = sb + sg8 + q;
+            if(s < ns) {
+                if(ok0) cfma(tot[q], T[s * M + j0], in0[q]);
+                if(ok1) cfma(tot[q], T[s * M + j1], in1[q]);
+            }
+        }
     }
+    // reduce over the 64 column-threads (2 warps) of each sample group
     #pragma unroll
-    for(int st = 0; st < RBM_ST; st++) {
-        const cplx r = warp_sum(tot[st]);
-        if((threadIdx.x & 31u) == 0) sm[st][threadIdx.x >> 5] = r;
+    for(int q = 0; q < 8; q++) {
+        const cplx r = warp_sum(tot[q]);
+        if((threadIdx.x & 31u) == 0) red[sg8 + q][(threadIdx.x >> 5) & 1u] = r;
     }
     __syncthreads();
-    if(threadIdx.x < RBM_ST && sb + threadIdx.x < ns) {
-        cplx r(0.0, 0.0);
-        for(int i = 0; i < 8; i++) r += sm[threadIdx.x][i];
-        a[sb + threadIdx.x] = r;
-    }
+    if(threadIdx.x < RBM_ST && sb + threadIdx.x < ns) a[sb + threadIdx.x] = red[threadIdx.x][0] + red[threadIdx.x][1];
 }
 
 // F_k = F'_k - E conj(Obar_k)      (TDVP.cu.template:300, 331-333)
@@ -279,6 +332,53 @@ __global__ void k_S_finalize(const cplx* __restrict__ Spart, unsigned splits, si
     }
 }
 
+// ============================================================================================ fused S.v tail and CG update
+// out_k = sum_ch part[ch][k] - conj(Obar_k) * dot + (shift_abs + shift_rel * diag_k) * v_k      (diag may be null)
+__global__ void k_sv_finish(const cplx* part, unsigned chunks, const cplx* __restrict__ Obar, const cplx* __restrict__ dot,
+                            const cplx* __restrict__ v, const double* __restrict__ diag, double shift_abs, double shift_rel,
+                            size_t P, cplx* out, bool correct) {   // part may alias out (chunks == 1)
+    const cplx d = *dot;
+    for(size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < P; k += (size_t)gridDim.x * blockDim.x) {
+        cplx a(0.0, 0.0);
+        for(unsigned c = 0; c < chunks; c++) a += part[(size_t)c * P + k];
+        if(correct) a -= conj(Obar[k]) * d;
+        if(diag) a += (shift_abs + shift_rel * diag[k]) * v[k];
+        out[k] = a;
+    }
+}
+// One CG iteration's vector work in ONE single-block kernel (n <= 64k): pAp -> alpha -> x, r -> |r|^2 -> beta -> p,
+// and the dot product Obar . p_new needed by the next S.v.   scal: [0] rs, [1] pAp, [2] rs_new, [3] Obar.p
+__global__ void __launch_bounds__(RED_T) k_cg_fused(cplx* __restrict__ x, cplx* __restrict__ r, cplx* __restrict__ p, const cplx* __restrict__ Ap,
+                                                    const cplx* __restrict__ Obar, cplx* __restrict__ scal, size_t n) {
+    __shared__ double bc[2];
+    double v[2] = {0, 0}, red[2];
+    for(size_t k = threadIdx.x; k < n; k += RED_T) { const cplx a = conj(p[k]) * Ap[k]; v[0] += a.re; v[1] += a.im; }
+    block_reduce<2>(v, red);
+    if(threadIdx.x == 0) { bc[0] = scal[0].re / red[0]; scal[1] = cplx(red[0], red[1]); }
+    __syncthreads();
+    const double alpha = bc[0];
+    v[0] = 0.0; v[1] = 0.0;
+    for(size_t k = threadIdx.x; k < n; k += RED_T) {
+        x[k] += alpha * p[k];
+        const cplx rk = r[k] - alpha * Ap[k];
+        r[k] = rk;
+        v[0] += abs2(rk);
+    }
+    block_reduce<2>(v, red);
+    if(threadIdx.x == 0) { bc[1] = red[0] / scal[0].re; scal[2] = cplx(red[0], 0.0); }
+    __syncthreads();
+    const double beta = bc[1];
+    v[0] = 0.0; v[1] = 0.0;
+    for(size_t k = threadIdx.x; k < n; k += RED_T) {
+        const cplx pk = r[k] + beta * p[k];
+        p[k] = pk;
+        const cplx d = Obar[k] * pk;
+        v[0] += d.re; v[1] += d.im;
+    }
+    block_reduce<2>(v, red);
+    if(threadIdx.x == 0) { scal[0] = scal[2]; scal[3] = cplx(red[0], red[1]); }
+}
+
 // ============================================================================================ solver kernels
 // scal layout (cplx): [0] rs_old, [1] pAp, [2] rs_new, [3] scratch
 __global__ void k_cg_xr(cplx* x, cplx* r, const cplx* p, const cplx* Ap, const cplx* scal, size_t n) {
@@ -307,20 +407,30 @@ __global__ void k_scale_vec(const cplx* in, cplx phase, cplx* out, size_t n, boo
 __global__ void k_conj_inplace(cplx* v, size_t n) {
     for(size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) v[k] = conj(v[k]);
 }
-// diag_k = sum_s w_s |O_sk|^2 - |Obar_k|^2
-__global__ void k_diag_dense(const cplx* __restrict__ O, const double* __restrict__ w, size_t ns, unsigned P, double* __restrict__ d) {
+// diag_k = sum_s w_s |O_sk|^2 - |Obar_k|^2 : per-chunk partials (blockIdx.y), summed in fixed order afterwards
+__global__ void k_diag_dense(const cplx* __restrict__ O, const double* __restrict__ w, size_t ns, unsigned P, size_t chunk, double* __restrict__ part) {
     const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
     if(k >= P) return;
+    const size_t s0 = (size_t)blockIdx.y * chunk, s1 = min(ns, s0 + chunk);
     double a = 0.0;
-    for(size_t s = 0; s < ns; s++) a = fma(w[s], abs2(O[s * P + k]), a);
-    d[k] = a;
+    for(size_t s = s0; s < s1; s++) a = fma(w[s], abs2(O[s * P + k]), a);
+    part[(size_t)blockIdx.y * P + k] = a;
 }
-__global__ void k_diag_rbm(const cplx* __restrict__ T, const double* __restrict__ w, size_t ns, unsigned N, unsigned M, double* __restrict__ d) {
+__global__ void k_diag_rbm(const cplx* __restrict__ T, const double* __restrict__ w, size_t ns, unsigned M, size_t chunk, double* __restrict__ part) {
     const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
     if(j >= M) return;
+    const size_t s0 = (size_t)blockIdx.y * chunk, s1 = min(ns, s0 + chunk);
     double a = 0.0;
-    for(size_t s = 0; s < ns; s++) a = fma(w[s], abs2(T[s * M + j]), a);
-    for(unsigned i = 0; i < N; i++) d[(size_t)i * M + j] = a;
+    for(size_t s = s0; s < s1; s++) a = fma(w[s], abs2(T[s * M + j]), a);
+    part[(size_t)blockIdx.y * M + j] = a;
+}
+// d[k] = sum_ch part[ch][k % period]   (period = M broadcasts the RBM's per-j value over the N sites)
+__global__ void k_diag_sum(const double* __restrict__ part, unsigned chunks, unsigned period, size_t n, double* __restrict__ d) {
+    for(size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+        double a = 0.0;
+        for(unsigned c = 0; c < chunks; c++) a += part[(size_t)c * period + (k % period)];
+        d[k] = a;
+    }
 }
 __global__ void k_diag_finalize(double* d, const cplx* Obar, size_t n) {
     for(size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) d[k] -= abs2(Obar[k]);
@@ -408,31 +518,40 @@ static unsigned pick_chunks(size_t ns, size_t col_blocks) {
     return (unsigned)ch;
 }
 
-// mean_out / x_out: [P] device; X: per-sample complex factor
-static void col_reduce(TDVP& t, const cplx* X, cplx* mean_out, cplx* x_out) {
+// per-chunk partial sums of mean_k = sum_s w_s O_sk and x_k = sum_s w_s X_s conj(O_sk) into t.chunk_buf
+struct ColPartials { unsigned chunks; cplx* mean; cplx* x; };
+static ColPartials col_reduce_partials(TDVP& t, const cplx* X, bool want_mean) {
     const size_t ns = t.S.ns; const unsigned P = t.P;
     if(ns == 0) {
-        if(mean_out) ANGPU_CUDA(cudaMemsetAsync(mean_out, 0, sizeof(cplx) * P, stream()));
-        ANGPU_CUDA(cudaMemsetAsync(x_out, 0, sizeof(cplx) * P, stream()));
-        return;
+        t.chunk_buf.resize((size_t)2 * P); t.chunk_buf.zero();
+        return ColPartials{1u, want_mean ? t.chunk_buf.p : nullptr, t.chunk_buf.p + P};
     }
     unsigned chunks; size_t chunk;
     if(t.factorised) {
         const unsigned jb = ceil_div(t.rbm_M, 128), ib = ceil_div(t.rbm_N, RBM_IT);
-        chunks = pick_chunks(ns, (size_t)jb * ib); chunk = (ns + chunks - 1) / chunks; chunks = (unsigned)((ns + chunk - 1) / chunk);
+        // chunks of whole 32-sample tiles; <= 64 chunks keeps the partial-sum traffic (chunks*P*16 B) small
+        chunks = (unsigned)std::max<size_t>(1, std::min<size_t>(64, (ns + RBM_TS - 1) / RBM_TS));
+        chunk = ((ns + chunks - 1) / chunks + RBM_TS - 1) / RBM_TS * RBM_TS; chunks = (unsigned)((ns + chunk - 1) / chunk);
         t.chunk_buf.resize((size_t)2 * chunks * P);
-        cplx* pm = mean_out ? t.chunk_buf.p : nullptr; cplx* px = t.chunk_buf.p + (size_t)chunks * P;
-        k_col_reduce_rbm<<<dim3(jb, ib, chunks), 128, 0, stream()>>>(t.S.conf.p, t.T.p, t.S.weight.p, X, ns, t.rbm_N, t.rbm_M, t.words, chunk, pm, px);
-    } else {
-        const unsigned cb = ceil_div(P, 128);
-        chunks = pick_chunks(ns, cb); chunk = (ns + chunks - 1) / chunks; chunks = (unsigned)((ns + chunk - 1) / chunk);
-        t.chunk_buf.resize((size_t)2 * chunks * P);
-        cplx* pm = mean_out ? t.chunk_buf.p : nullptr; cplx* px = t.chunk_buf.p + (size_t)chunks * P;
-        k_col_reduce_dense<<<dim3(cb, chunks), 128, 0, stream()>>>(t.O.p, t.S.weight.p, X, ns, P, chunk, pm, px);
+        cplx* pm = want_mean ? t.chunk_buf.p : nullptr; cplx* px = t.chunk_buf.p + (size_t)chunks * P;
+        if(want_mean) k_col_reduce_rbm<true><<<dim3(jb, ib, chunks), 128, 0, stream()>>>(t.S.conf.p, t.T.p, t.S.weight.p, X, ns, t.rbm_N, t.rbm_M, t.words, chunk, pm, px);
+        else k_col_reduce_rbm<false><<<dim3(jb, ib, chunks), 128, 0, stream()>>>(t.S.conf.p, t.T.p, t.S.weight.p, X, ns, t.rbm_N, t.rbm_M, t.words, chunk, pm, px);
+        ANGPU_CHECK_LAUNCH(); count_launch();
+        return ColPartials{chunks, pm, px};
     }
+    const unsigned cb = ceil_div(P, 128);
+    chunks = pick_chunks(ns, cb); chunk = (ns + chunks - 1) / chunks; chunks = (unsigned)((ns + chunk - 1) / chunk);
+    t.chunk_buf.resize((size_t)2 * chunks * P);
+    cplx* pm = want_mean ? t.chunk_buf.p : nullptr; cplx* px = t.chunk_buf.p + (size_t)chunks * P;
+    k_col_reduce_dense<<<dim3(cb, chunks), 128, 0, stream()>>>(t.O.p, t.S.weight.p, X, ns, P, chunk, pm, px);
     ANGPU_CHECK_LAUNCH(); count_launch();
-    if(mean_out) { k_sum_chunks<<<grid_for(P), 256, 0, stream()>>>(t.chunk_buf.p, chunks, P, mean_out); ANGPU_CHECK_LAUNCH(); count_launch(); }
-    k_sum_chunks<<<grid_for(P), 256, 0, stream()>>>(t.chunk_buf.p + (size_t)chunks * P, chunks, P, x_out);
+    return ColPartials{chunks, pm, px};
+}
+// mean_out / x_out: [P] device; X: per-sample complex factor
+static void col_reduce(TDVP& t, const cplx* X, cplx* mean_out, cplx* x_out) {
+    const ColPartials cp = col_reduce_partials(t, X, mean_out != nullptr);
+    if(mean_out) { k_sum_chunks<<<grid_for(t.P), 256, 0, stream()>>>(cp.mean, cp.chunks, t.P, mean_out); ANGPU_CHECK_LAUNCH(); count_launch(); }
+    k_sum_chunks<<<grid_for(t.P), 256, 0, stream()>>>(cp.x, cp.chunks, t.P, x_out);
     ANGPU_CHECK_LAUNCH(); count_launch();
 }
 
@@ -492,6 +611,7 @@ void TDVP::ensure_dense_O(Psi* psi) {
 void TDVP::build_S() {
     ANGPU_REQUIRE(evaluated, "TDVP: call eval first");
     ensure_dense_O(last_psi);
+    mark(5);
     Smat.resize((size_t)P * P);
     const unsigned nt = (P + ZT - 1) / ZT, tiles = nt * (nt + 1) / 2;
     const size_t ns = S.ns;
@@ -519,9 +639,12 @@ void TDVP::build_S() {
     k_S_finalize<<<grid_for(stride), 256, 0, stream()>>>(Smat.p, 1, stride, Ok_dev(), P, Smat.p, true);
     ANGPU_CHECK_LAUNCH(); count_launch();
     have_S = true;
+    mark(6);
+    if(profile) { ANGPU_CUDA(cudaEventSynchronize(ev[6])); ANGPU_CUDA(cudaEventElapsedTime(&phase_ms[4], ev[5], ev[6])); }
 }
 
-void TDVP::S_dot_vector_dev(const cplx* v_dev, cplx* out_dev) {
+// out = S v (+ (shift_abs + shift_rel diag) v when diag != null).  dot_dev: device scalar Obar . v if already known.
+void TDVP::matvec(const cplx* v_dev, cplx* out_dev, const cplx* dot_dev, const double* diag, double shift_abs, double shift_rel) {
     ANGPU_REQUIRE(evaluated, "TDVP: call eval / eval_F first");
     const size_t ns = S.ns;
     row_a.resize(std::max<size_t>(1, ns));
@@ -530,15 +653,25 @@ void TDVP::S_dot_vector_dev(const cplx* v_dev, cplx* out_dev) {
         else k_rowdot_dense<<<(unsigned)ns, 256, 0, stream()>>>(O.p, v_dev, P, row_a.p);
         ANGPU_CHECK_LAUNCH(); count_launch();
     }
-    col_reduce(*this, row_a.p, nullptr, out_dev);
-    allreduce_sum(reinterpret_cast<double*>(out_dev), 2 * (size_t)P);
     d_scal.resize(16);
-    cplx* dot = reinterpret_cast<cplx*>(d_scal.p) + 4;
-    k_dot<false><<<1, RED_T, 0, stream()>>>(Ok_dev(), v_dev, P, dot);
-    ANGPU_CHECK_LAUNCH(); count_launch();
-    k_sv_correct<<<grid_for(P), 256, 0, stream()>>>(Ok_dev(), dot, P, out_dev);
+    if(!dot_dev) {
+        cplx* dot = reinterpret_cast<cplx*>(d_scal.p) + 4;
+        k_dot<false><<<1, RED_T, 0, stream()>>>(Ok_dev(), v_dev, P, dot);
+        ANGPU_CHECK_LAUNCH(); count_launch();
+        dot_dev = dot;
+    }
+    const ColPartials cp = col_reduce_partials(*this, row_a.p, false);
+    if(has_allreduce()) {
+        k_sum_chunks<<<grid_for(P), 256, 0, stream()>>>(cp.x, cp.chunks, P, out_dev);
+        ANGPU_CHECK_LAUNCH(); count_launch();
+        allreduce_sum(reinterpret_cast<double*>(out_dev), 2 * (size_t)P);
+        k_sv_finish<<<grid_for(P), 256, 0, stream()>>>(out_dev, 1u, Ok_dev(), dot_dev, v_dev, diag, shift_abs, shift_rel, P, out_dev, true);
+    } else {
+        k_sv_finish<<<grid_for(P), 256, 0, stream()>>>(cp.x, cp.chunks, Ok_dev(), dot_dev, v_dev, diag, shift_abs, shift_rel, P, out_dev, true);
+    }
     ANGPU_CHECK_LAUNCH(); count_launch();
 }
+void TDVP::S_dot_vector_dev(const cplx* v_dev, cplx* out_dev) { matvec(v_dev, out_dev, nullptr, nullptr, 0.0, 0.0); }
 void TDVP::S_dot_vector(const cplx* v_host, cplx* out_host) {
     vec_in.upload(v_host, P);
     vec_out.resize(P);
@@ -549,16 +682,25 @@ void TDVP::S_dot_vector(const cplx* v_host, cplx* out_host) {
 static void tdvp_diag(TDVP& t, DevBuf<double>& dbuf) {
     dbuf.resize(t.P);
     const size_t ns = t.S.ns;
-    if(t.factorised) k_diag_rbm<<<ceil_div(t.rbm_M, 128), 128, 0, stream()>>>(t.T.p, t.S.weight.p, ns, t.rbm_N, t.rbm_M, dbuf.p);
-    else k_diag_dense<<<ceil_div(t.P, 128), 128, 0, stream()>>>(t.O.p, t.S.weight.p, ns, t.P, dbuf.p);
-    ANGPU_CHECK_LAUNCH(); count_launch();
+    const unsigned period = t.factorised ? t.rbm_M : t.P;
+    unsigned chunks = (unsigned)std::max<size_t>(1, std::min<size_t>(256, ns / 64));
+    const size_t chunk = ns ? (ns + chunks - 1) / chunks : 1;
+    chunks = ns ? (unsigned)((ns + chunk - 1) / chunk) : 1;
+    DevBuf<double> part((size_t)chunks * period);
+    if(ns == 0) part.zero();
+    else if(t.factorised) k_diag_rbm<<<dim3(ceil_div(period, 128), chunks), 128, 0, stream()>>>(t.T.p, t.S.weight.p, ns, t.rbm_M, chunk, part.p);
+    else k_diag_dense<<<dim3(ceil_div(period, 128), chunks), 128, 0, stream()>>>(t.O.p, t.S.weight.p, ns, t.P, chunk, part.p);
+    k_diag_sum<<<grid_for(t.P), 256, 0, stream()>>>(part.p, chunks, period, t.P, dbuf.p);
+    ANGPU_CHECK_LAUNCH(); count_launch(2);
     allreduce_sum(dbuf.p, t.P);
     k_diag_finalize<<<grid_for(t.P), 256, 0, stream()>>>(dbuf.p, t.Ok_dev(), t.P);
     ANGPU_CHECK_LAUNCH(); count_launch();
+    ANGPU_CUDA(cudaStreamSynchronize(stream()));      // `part` is freed on return
 }
 
 int TDVP::solve_cg(double tol, unsigned max_iter, double shift_abs, double shift_rel, cplx rhs_phase, cplx* x_host, double* rel_res_out) {
     ANGPU_REQUIRE(evaluated, "TDVP: call eval / eval_F first");
+    mark(5);
     const size_t n = P;
     DevBuf<double> dg;
     if(shift_rel != 0.0) tdvp_diag(*this, dg); else { dg.resize(n); dg.zero(); }
@@ -572,33 +714,50 @@ int TDVP::solve_cg(double tol, unsigned max_iter, double shift_abs, double shift
     ANGPU_CUDA(cudaMemcpyAsync(p, b, sizeof(cplx) * n, cudaMemcpyDeviceToDevice, stream()));
     k_dot<true><<<1, RED_T, 0, stream()>>>(r, r, n, scal + 0);
     count_launch(2);
-    cplx h; ANGPU_CUDA(cudaMemcpyAsync(&h, scal, sizeof(cplx), cudaMemcpyDeviceToHost, stream()));
-    ANGPU_CUDA(cudaStreamSynchronize(stream()));
-    const double b2 = h.re;
+    // convergence is decided on values summed over ranks, so that every rank takes the same decision
+    auto read_rs = [&]() -> double {
+        double* chk = d_scal.p + 12;
+        ANGPU_CUDA(cudaMemcpyAsync(chk, scal, sizeof(double), cudaMemcpyDeviceToDevice, stream()));
+        allreduce_sum(chk, 1);
+        double hv = 0.0;
+        ANGPU_CUDA(cudaMemcpyAsync(&hv, chk, sizeof(double), cudaMemcpyDeviceToHost, stream()));
+        ANGPU_CUDA(cudaStreamSynchronize(stream()));
+        return hv;
+    };
+    cplx h(0.0, 0.0);
+    const double b2 = read_rs();
     if(rel_res_out) *rel_res_out = 0.0;
     unsigned it = 0;
     if(b2 > 0.0) {
         const unsigned check_every = 8;
+        const bool fused = n <= 65536;
+        if(fused) { k_dot<false><<<1, RED_T, 0, stream()>>>(Ok_dev(), p, n, scal + 3); ANGPU_CHECK_LAUNCH(); count_launch(); }
         for(it = 1; it <= max_iter; it++) {
-            S_dot_vector_dev(p, Ap);
-            k_add_shift<<<grid_for(n), 256, 0, stream()>>>(Ap, p, dg.p, shift_abs, shift_rel, n);
-            k_dot<true><<<1, RED_T, 0, stream()>>>(p, Ap, n, scal + 1);
-            k_cg_xr<<<grid_for(n), 256, 0, stream()>>>(x, r, p, Ap, scal, n);
-            k_dot<true><<<1, RED_T, 0, stream()>>>(r, r, n, scal + 2);
-            k_cg_p<<<grid_for(n), 256, 0, stream()>>>(p, r, scal, n);
-            k_cg_roll<<<1, 1, 0, stream()>>>(scal);
-            ANGPU_CHECK_LAUNCH(); count_launch(6);
+            if(fused) {
+                matvec(p, Ap, scal + 3, dg.p, shift_abs, shift_rel);
+                k_cg_fused<<<1, RED_T, 0, stream()>>>(x, r, p, Ap, Ok_dev(), scal, n);
+                ANGPU_CHECK_LAUNCH(); count_launch();
+            } else {
+                matvec(p, Ap, nullptr, dg.p, shift_abs, shift_rel);
+                k_dot<true><<<1, RED_T, 0, stream()>>>(p, Ap, n, scal + 1);
+                k_cg_xr<<<grid_for(n), 256, 0, stream()>>>(x, r, p, Ap, scal, n);
+                k_dot<true><<<1, RED_T, 0, stream()>>>(r, r, n, scal + 2);
+                k_cg_p<<<grid_for(n), 256, 0, stream()>>>(p, r, scal, n);
+                k_cg_roll<<<1, 1, 0, stream()>>>(scal);
+                ANGPU_CHECK_LAUNCH(); count_launch(5);
+            }
             if(it % check_every == 0 || it == max_iter) {
-                ANGPU_CUDA(cudaMemcpyAsync(&h, scal, sizeof(cplx), cudaMemcpyDeviceToHost, stream()));
-                ANGPU_CUDA(cudaStreamSynchronize(stream()));
+                h.re = read_rs();
                 if(rel_res_out) *rel_res_out = std::sqrt(h.re / b2);
                 if(h.re <= tol * tol * b2) break;
             }
         }
         if(it > max_iter) it = max_iter;
     }
+    mark(6);
     ANGPU_CUDA(cudaMemcpyAsync(x_host, x, sizeof(cplx) * n, cudaMemcpyDeviceToHost, stream()));
     ANGPU_CUDA(cudaStreamSynchronize(stream()));
+    if(profile) ANGPU_CUDA(cudaEventElapsedTime(&phase_ms[5], ev[5], ev[6]));
     return (int)it;
 }
 
@@ -606,6 +765,7 @@ static cusolverDnHandle_t g_cusolver = nullptr;
 void TDVP::solve_dense(double shift_abs, double shift_rel, cplx rhs_phase, cplx* x_host) {
     ANGPU_REQUIRE(evaluated, "TDVP: call eval first");
     if(!have_S) build_S();
+    mark(5);
     const size_t n = P;
     DevBuf<double> dg;
     if(shift_rel != 0.0) tdvp_diag(*this, dg); else { dg.resize(n); dg.zero(); }
@@ -628,7 +788,9 @@ void TDVP::solve_dense(double shift_abs, double shift_rel, cplx rhs_phase, cplx*
     if(cusolverDnZpotrs(g_cusolver, CUBLAS_FILL_MODE_LOWER, (int)n, 1, Ad, (int)n, bd, (int)n, info.p) != CUSOLVER_STATUS_SUCCESS) throw Error("Zpotrs failed");
     k_conj_inplace<<<grid_for(n), 256, 0, stream()>>>(b.p, n);
     ANGPU_CHECK_LAUNCH(); count_launch();
+    mark(6);
     b.download(x_host, n);
+    if(profile) ANGPU_CUDA(cudaEventElapsedTime(&phase_ms[5], ev[5], ev[6]));
 }
 
 // ============================================================================================ FP64 peak probe

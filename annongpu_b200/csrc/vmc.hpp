@@ -16,6 +16,7 @@ namespace angpu {
 typedef void (*allreduce_fn)(void* dev_ptr, unsigned long long count, void* user);
 void set_allreduce(allreduce_fn fn, void* user);
 void allreduce_sum(double* dev_ptr, size_t count);
+bool has_allreduce();
 
 struct Ensemble {
     bool is_mc = false;
@@ -81,16 +82,20 @@ struct TDVP {
     void ensure_dense_O(Psi* psi);
     // out = S v using the samples of the last eval (TDVP::S_dot_vector, :337-443), O(ns*P) instead of the reference's O(ns*P^2)
     void S_dot_vector_dev(const cplx* v_dev, cplx* out_dev);
+    void matvec(const cplx* v_dev, cplx* out_dev, const cplx* dot_dev, const double* diag, double shift_abs, double shift_rel);
     void S_dot_vector(const cplx* v_host, cplx* out_host);
     // NEW (no reference counterpart): solve (S + shift_abs*I + shift_rel*diag(S)) x = rhs_phase * F
     int  solve_cg(double tol, unsigned max_iter, double shift_abs, double shift_rel, cplx rhs_phase, cplx* x_host, double* rel_res_out);
     void solve_dense(double shift_abs, double shift_rel, cplx rhs_phase, cplx* x_host);
     void build_S();
+    // opt-in fast path: 3xTF32 on tcgen05 tensor cores (sbuild_tc.cu), ~1e-5 relative to ||S||
+    void build_S_tensorcore();
+    DevBuf<float> tc_planes;
     Psi* last_psi = nullptr;
     // optional phase timing (bench.py): CUDA events on the library stream around sample / E_loc / O_k+reduce
     bool profile = false;
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    float phase_ms[4] = {0, 0, 0, 0};     // sample, eloc, ok+reduce(+allreduce), total
+    cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float phase_ms[6] = {0, 0, 0, 0, 0, 0};     // sample, eloc, ok+reduce(+allreduce), total, S build, last solve
     void mark(int i);
     ~TDVP();
 };

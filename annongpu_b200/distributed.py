@@ -9,12 +9,16 @@ points; the hook wraps the device pointer in a torch tensor (no copy) and runs `
 
 The reference has no counterpart (single device, no collectives — SURVEY.md §2).
 """
+import datetime
 import os
 
 import torch
 import torch.distributed as dist
 
 from . import api
+
+
+_stream = None
 
 
 class _DevArray:
@@ -42,17 +46,25 @@ def init_from_env(backend="nccl"):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     api.setDevice(local_rank)
-    # run the library on torch's current stream so that NCCL work and torch.cuda.Event timing are ordered with it
-    api.set_stream(torch.cuda.current_stream().cuda_stream)
+    # Run the library on a dedicated torch stream made current: NCCL collectives issued by the hook and torch.cuda.Event
+    # timing are then ordered with the library's kernels.  (torch's default stream has handle 0, which the C ABI reads
+    # as "use your own stream" — never pass it.)
+    global _stream
+    _stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(_stream)
+    api.set_stream(_stream.cuda_stream)
     if world > 1:
         if not dist.is_initialized():
             dist.init_process_group(backend=backend, rank=rank, world_size=world,
-                                    device_id=torch.device("cuda", local_rank))
+                                    device_id=torch.device("cuda", local_rank),
+                                    timeout=datetime.timedelta(seconds=int(os.environ.get("ANGPU_NCCL_TIMEOUT_S", "120"))))
         api.set_allreduce(allreduce_hook)
     return rank, world
 
 
 def shutdown():
     api.set_allreduce(None)
+    api.synchronize()
+    api.set_stream(None)
     if dist.is_initialized():
         dist.destroy_process_group()

@@ -239,8 +239,9 @@ def run_ours(args):
     proposals = (THERM + SWEEPS) * N
     # algorithmic HBM bytes of one launch: W read once + per chain (conf + log_psi + M cached angles) written
     hbm_bytes = N * M * 16 + chains_local * (8 * words + 16 + 16 * M)
-    # algorithmic flops: per proposal and hidden unit 22 (angle update 4 + Re lc0: 18), real final weight
-    flops = chains_local * proposals * M * 22.0
+    # algorithmic flops: per proposal and hidden unit 18 (angle update 2 FMA = 4, Re lc0 in (p, q) form: 14; real final
+    # weight); the undo on rejection and the fp32-screened acceptance are not counted
+    flops = chains_local * proposals * M * 18.0
     hbm_peak, peak_src = measured_peaks()
     fp64_peak = A.measure_fp64_tflops()
     roofline = {"kernel": "k_mc_rbm<8,true>", "bound": "hbm", "achieved": hbm_bytes / t_sample / 1e9, "peak": hbm_peak,

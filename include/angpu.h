@@ -162,11 +162,15 @@ int angpu_tdvp_S_dot_vector(angpu_tdvp_t tdvp, const double* vec, double* out); 
 int angpu_tdvp_solve_cg(angpu_tdvp_t tdvp, double tol, unsigned max_iter, double shift_abs, double shift_rel,
                         const double rhs_phase[2], double* x_out, unsigned* iterations_out, double* rel_residual_out);
 int angpu_tdvp_solve_dense(angpu_tdvp_t tdvp, double shift_abs, double shift_rel, const double rhs_phase[2], double* x_out);
+/* NEW, opt-in: rebuild S from the samples of the last eval on the tcgen05 tensor cores (3xTF32 split, fp32 accumulation in
+ * TMEM; ~1e-5 relative to ||S||).  angpu_tdvp_eval itself builds S in exact fp64 (the reference: fp64 atomics, :216-279). */
+int angpu_tdvp_build_S_tensorcore(angpu_tdvp_t tdvp);
 
 /* ---- measurement aids (no reference counterpart) -------------------------------------------------------- */
-/* CUDA-event timing of the phases of the last eval / eval_F on the library stream: {sampling, E_loc, O_k + reductions, total} ms */
+/* CUDA-event timing on the library stream, ms: {sampling, E_loc, O_k + reductions, eval total} of the last eval / eval_F,
+ * {S build, last solve_cg / solve_dense} */
 int angpu_tdvp_set_profile(angpu_tdvp_t tdvp, int enable);
-int angpu_tdvp_phase_ms(angpu_tdvp_t tdvp, double out[4]);
+int angpu_tdvp_phase_ms(angpu_tdvp_t tdvp, double out[6]);
 /* measured FP64 FMA throughput of the device (TFLOP/s), the roofline denominator of the FP64-pipe-bound kernels */
 int angpu_measure_fp64_tflops(double* out);
 

@@ -322,3 +322,33 @@ def test_c5_properties(gpu, port):
     assert rel_err(lp[idx], lp_p) <= TOL and rel_err(t.E_local_samples[idx], el_p) <= TOL
     x, it, rr = t.solve_cg(tol=1e-6, max_iter=300, shift_abs=0.0, shift_rel=1e-3)
     assert rr <= 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ tensor-core S build
+
+@pytest.mark.parametrize("name,ns_mc", [("deep2", 0), ("rbm12_m40", 0), ("deep2", 3000)])
+def test_tensorcore_S_build_matches_fp64(gpu, name, ns_mc):
+    """The opt-in tcgen05 path (3xTF32 split, fp32 accumulation in TMEM) against the exact fp64 S of the same samples:
+    tolerance 1e-5 relative to ||S|| (BASELINE.json's fp32 tolerance); Hermitian to rounding."""
+    spec, H, N = zoo()[name]
+    psi, op = make_psi(gpu, spec), make_op(gpu, H)
+    if ns_mc:
+        ens = gpu.MonteCarloSpins(ns_mc, 1, 5, ns_mc, True, seed=11)
+    else:
+        ens = gpu.ExactSummationSpins(N)
+        psi.normalize(ens)
+    t = gpu.TDVP(psi.num_params, True)
+    t.eval(op, psi, ens)
+    S64 = t.S_matrix
+    t.build_S_tensorcore()
+    S32 = t.S_matrix
+    scale = np.abs(S64).max()
+    assert np.abs(S32 - S64).max() <= 1e-5 * scale
+    assert np.abs(S32 - S32.conj().T).max() <= 1e-12 * scale
+    # un-normalised ExactSummation weights (sum w != 1): the reference's convention S = sum w O*O - <O>*<O> is kept
+    if not ns_mc:
+        psi.log_prefactor = psi.log_prefactor + 0.3
+        t.eval(op, psi, ens)
+        S64 = t.S_matrix
+        t.build_S_tensorcore()
+        assert np.abs(t.S_matrix - S64).max() <= 1e-5 * np.abs(S64).max()
