@@ -17,7 +17,9 @@
 //                                      (box 16 fp32 x 128 rows, 64B swizzle), 3 stages x 64 KB
 //           warp 1      MMA issuer     12 x (BLOCK_K/8) tcgen05.mma.kind::tf32 per stage into two 128x128 fp32
 //                                      accumulators in TMEM (Re S, Im S; Im uses the negate-A bit), tcgen05.commit -> mbarrier
-//           warps 2-5   epilogue       tcgen05.ld 32x32b -> fp64 -> S[r][c] and its Hermitian mirror S[c][r]
+//           warps 2-17  epilogue       every 128 samples: tcgen05.ld 32x32b of the finished accumulator set, added with
+//                                      round-to-nearest into fp32 registers (the tensor core's own fp32 accumulation
+//                                      truncates); at the end fp64 -> S[r][c] and its Hermitian mirror S[c][r]
 #include "vmc.hpp"
 #include <cuda.h>
 #include <cmath>
@@ -34,8 +36,11 @@ constexpr int TILE_BYTES = BLOCK_MN * BLOCK_K * 4;            // 8 KB
 constexpr int TILES_PER_STAGE = 8;
 constexpr int STAGE_BYTES = TILES_PER_STAGE * TILE_BYTES;     // 64 KB
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
-constexpr int TMEM_COLS = 256;      // two 128-column fp32 accumulators
-constexpr int THREADS = 192;
+// barriers: full[STAGES] | empty[STAGES] | tmem_full[2] | tmem_empty[2] | tmem base slot
+constexpr int TMEM_COLS = 512;      // 2 ping-pong sets x (Re, Im) 128-column fp32 accumulators
+constexpr int CHUNK_KB = 8;         // k-blocks (x16 samples) accumulated in TMEM before the epilogue drains the set
+constexpr int EPI_WARPS = 16;       // 4 lane quarters x 4 column groups of 32
+constexpr int THREADS = 64 + 32 * EPI_WARPS;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -99,8 +104,9 @@ k_sbuild_tf32(const __grid_constant__ Maps maps, unsigned P, unsigned num_kb, cp
     // 1024-byte aligned tile area, then the barriers
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t tiles = (raw + 1023u) & ~1023u;
-    const uint32_t bars = tiles + STAGES * STAGE_BYTES;          // full[STAGES], empty[STAGES], tmem_full, tmem_ptr
-    const uint32_t bar_full = bars, bar_empty = bars + 8u * STAGES, bar_tmem = bars + 16u * STAGES, tmem_slot = bar_tmem + 8u;
+    const uint32_t bars = tiles + STAGES * STAGE_BYTES;
+    const uint32_t bar_full = bars, bar_empty = bars + 8u * STAGES, bar_tfull = bars + 16u * STAGES, bar_tempty = bar_tfull + 16u,
+                   tmem_slot = bar_tempty + 16u;
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
 
     // upper-triangular tile pair
@@ -112,7 +118,7 @@ k_sbuild_tf32(const __grid_constant__ Maps maps, unsigned P, unsigned num_kb, cp
 
     if(threadIdx.x == 0) {
         for(int s = 0; s < STAGES; s++) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, 1); }
-        mbar_init(bar_tmem, 1);
+        for(int q = 0; q < 2; q++) { mbar_init(bar_tfull + 8u * q, 1); mbar_init(bar_tempty + 8u * q, EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if(warp == 1) {
@@ -146,9 +152,15 @@ k_sbuild_tf32(const __grid_constant__ Maps maps, unsigned P, unsigned num_kb, cp
         // ------------------------------------------------------------------ MMA issuer
         if(lane == 0) {
             const uint32_t id_pos = umma_idesc_tf32(false), id_neg = umma_idesc_tf32(true);
-            const uint32_t acc_re = tmem_base, acc_im = tmem_base + (uint32_t)BLOCK_MN;
             for(unsigned kb = 0; kb < num_kb; kb++) {
                 const unsigned s = kb % STAGES, ph = (kb / STAGES) & 1u;
+                const unsigned chunk = kb / CHUNK_KB, set = chunk & 1u, in_chunk = kb % CHUNK_KB;
+                const uint32_t acc_re = tmem_base + set * 2u * BLOCK_MN, acc_im = acc_re + (uint32_t)BLOCK_MN;
+                if(in_chunk == 0) {
+                    // the epilogue must have drained this accumulator set (first use of each set passes immediately)
+                    mbar_wait(bar_tempty + 8u * set, ((chunk >> 1) & 1u) ^ 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
                 mbar_wait(bar_full + 8u * s, ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t base = tiles + s * STAGE_BYTES;
@@ -159,7 +171,7 @@ k_sbuild_tf32(const __grid_constant__ Maps maps, unsigned P, unsigned num_kb, cp
                     uint64_t d[8];
                     #pragma unroll
                     for(int q = 0; q < 8; q++) d[q] = umma_desc_sw64(base + (uint32_t)q * TILE_BYTES + koff);
-                    const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
+                    const uint32_t first = (in_chunk == 0 && k == 0) ? 0u : 1u;
                     // Re S += Re_r.Re_c + Im_r.Im_c      (hi.hi + hi.lo + lo.hi each)
                     umma_tf32(acc_re, d[0], d[4], id_pos, first);
                     umma_tf32(acc_re, d[0], d[5], id_pos, 1u);
@@ -176,32 +188,51 @@ k_sbuild_tf32(const __grid_constant__ Maps maps, unsigned P, unsigned num_kb, cp
                     umma_tf32(acc_im, d[3], d[4], id_neg, 1u);
                 }
                 umma_commit(bar_empty + 8u * s);            // frees the stage when these MMAs have read it
+                if(in_chunk == CHUNK_KB - 1 || kb == num_kb - 1) umma_commit(bar_tfull + 8u * set);   // chunk accumulated
             }
-            umma_commit(bar_tmem);                          // accumulators complete
         }
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        // ------------------------------------------------------------------ epilogue (warps 2..17)
+        // The tensor core accumulates in fp32 with truncation, so a long sum over the samples drifts (~n * 2^-24): every
+        // CHUNK_KB k-blocks the accumulator set is drained and added, with round-to-nearest, into fp32 registers while the
+        // MMA warp fills the other set.  Thread = one row (TMEM lane), 32 of the 128 columns, Re and Im.
         const unsigned quarter = warp & 3u;                 // TMEM lane quarter this warp may access
-        mbar_wait(bar_tmem, 0u);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const unsigned m_local = quarter * 32u + lane;
-        const unsigned r = (unsigned)row0 + m_local;
-        #pragma unroll 1
-        for(int c16 = 0; c16 < BLOCK_MN / 16; c16++) {
-            uint32_t vre[16], vim[16];
-            const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + (uint32_t)(c16 * 16);
-            tmem_ld16(taddr, vre);
-            tmem_ld16(taddr + (uint32_t)BLOCK_MN, vim);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if(r < P) {
+        const unsigned part = (warp - 2u) >> 2;             // 32-column group
+        float accR[32], accI[32];
+        #pragma unroll
+        for(int j = 0; j < 32; j++) { accR[j] = 0.0f; accI[j] = 0.0f; }
+        const unsigned num_chunks = (num_kb + CHUNK_KB - 1) / CHUNK_KB;
+        for(unsigned chunk = 0; chunk < num_chunks; chunk++) {
+            const unsigned set = chunk & 1u;
+            mbar_wait(bar_tfull + 8u * set, (chunk >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tre = tmem_base + ((quarter * 32u) << 16) + set * 2u * BLOCK_MN + part * 32u;
+            #pragma unroll
+            for(int c16 = 0; c16 < 2; c16++) {
+                uint32_t v[16];
+                tmem_ld16(tre + (uint32_t)(c16 * 16), v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 #pragma unroll
-                for(int j = 0; j < 16; j++) {
-                    const unsigned c = (unsigned)col0 + (unsigned)(c16 * 16 + j);
-                    if(c < P) {
-                        const cplx v((double)__uint_as_float(vre[j]), (double)__uint_as_float(vim[j]));
-                        if(tr != tc_) { S[(size_t)r * P + c] = v; S[(size_t)c * P + r] = conj(v); }
-                        else if(c >= r) { S[(size_t)r * P + c] = v; if(c != r) S[(size_t)c * P + r] = conj(v); }
-                    }
+                for(int j = 0; j < 16; j++) accR[c16 * 16 + j] += __uint_as_float(v[j]);
+                tmem_ld16(tre + (uint32_t)BLOCK_MN + (uint32_t)(c16 * 16), v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                #pragma unroll
+                for(int j = 0; j < 16; j++) accI[c16 * 16 + j] += __uint_as_float(v[j]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if(lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_tempty + 8u * set) : "memory");
+        }
+        const unsigned r = (unsigned)row0 + quarter * 32u + lane;
+        if(r < P) {
+            #pragma unroll
+            for(int j = 0; j < 32; j++) {
+                const unsigned c = (unsigned)col0 + part * 32u + (unsigned)j;
+                if(c < P) {
+                    const cplx v((double)accR[j], (double)accI[j]);
+                    if(tr != tc_) { S[(size_t)r * P + c] = v; S[(size_t)c * P + r] = conj(v); }
+                    else if(c > r) { S[(size_t)r * P + c] = v; S[(size_t)c * P + r] = conj(v); }
+                    else if(c == r) S[(size_t)r * P + c] = cplx(v.re, 0.0);      // diagonal of a Hermitian matrix: exactly real
                 }
             }
         }

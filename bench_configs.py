@@ -81,15 +81,29 @@ def main():
         t.set_profile(True)
         ms_eval = timed(lambda: t.eval(op, psi, mc), args.steps, warmup=1)
         ph = t.phase_ms
-        t0 = time.perf_counter()
         x = t.solve(shift_abs=0.0, shift_rel=1e-3)
         ms_solve = t.phase_ms["solve"]
         flops_S = 4.0 * ns * P * P
+        # opt-in tensor-core rebuild of S from the same samples (3xTF32 on tcgen05): time and deviation from the fp64 S
+        import numpy as np
+        S64 = t.S_matrix
+        tc_ms = []
+        for _ in range(3):
+            t.build_S_tensorcore()
+            tc_ms.append(t.phase_ms["s_build"])
+        S32 = t.S_matrix
+        tc_err = float(np.abs(S32 - S64).max() / np.abs(S64).max())
+        del S64, S32
+        mma_flops = 12.0 * ns * P * P            # 12 real 128x128x8 products per k-step on the upper-triangular tile pairs
+        tc = {"ms": min(tc_ms), "equivalent fp64 TFLOP/s (4 Ns P^2)": flops_S / (min(tc_ms) * 1e-3) / 1e12,
+              "issued tf32 TFLOP/s (12 Ns P^2)": mma_flops / (min(tc_ms) * 1e-3) / 1e12, "max rel deviation from fp64 S": tc_err,
+              "includes": "fp64 centring + TF32 hi/lo packing (k_pack_planes) + k_sbuild_tf32"}
         print(json.dumps({"config": "C4", "what": "PsiDeep 64->64->64 (P=8384), 8x8 TFIM (192 strings), TDVP.eval: sampling + E_loc + O_k + dense S, "
                           "then Cholesky solve", "samples": ns, "ms_eval": ms_eval, "sr_steps_per_s": 1e3 / (ms_eval + ms_solve),
                           "phase_ms": ph, "ms_dense_solve": ms_solve,
                           "S_build": {"ms": ph["s_build"], "TFLOP/s (4 Ns P^2)": flops_S / (ph["s_build"] * 1e-3) / 1e12,
                                       "fp64_peak_measured": fp64_peak, "frac_of_fp64_peak": flops_S / (ph["s_build"] * 1e-3) / 1e12 / fp64_peak},
+                          "S_build_tensorcore": tc,
                           "acceptance": mc.acceptance_rate, "E": t.E_local.real, "x_norm": float(abs(x).max())}))
 
     if "C5" in todo:
