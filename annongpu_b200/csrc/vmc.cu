@@ -251,6 +251,136 @@ __global__ void __launch_bounds__(256) k_rowdot_rbm(const uint64_t* __restrict__
     if(threadIdx.x < RBM_ST && sb + threadIdx.x < ns) a[sb + threadIdx.x] = red[threadIdx.x][0] + red[threadIdx.x][1];
 }
 
+// ============================================================================================ FP64 tensor-core (DMMA) mat-vec
+// The factorised S.v is two GEMMs against the +-1 spin matrix sigma [ns][N]:
+//     U = sigma V            a_s = sum_j T_sj U_sj                     (k_rowdot_dmma)
+//     Y = sigma^T Z          Z_sj = w_s a_s conj(T_sj)                 (k_colreduce_dmma, per-chunk partials)
+// with complex matrices viewed as real ones with 2M columns ((re, im) adjacent).  Both run on the FP64 tensor cores
+// (mma.sync.m8n8k4.f64: exact fp64 products and accumulation, so S.v keeps its 1e-10 parity), the +-1 operand is
+// generated from the configuration bits in registers, the other operand is staged in shared memory.
+// Fragment layout (PTX ISA, m8n8k4 .f64): A[row = lane>>2][k = lane&3], B[k = lane&3][col = lane>>2],
+// C/D[row = lane>>2][col = 2*(lane&3) + {0,1}]  =>  each lane ends up with ONE complex number per 8x8 tile.
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double bit_sign(const uint64_t* cw, unsigned i) { return ((cw[i >> 6] >> (i & 63u)) & 1ull) ? 1.0 : -1.0; }
+
+constexpr int RD_WARPS = 4, RD_KC = 32, RD_CB = 128, RD_PAD = 8;      // 32 samples per block, 128 real columns per pass
+__global__ void __launch_bounds__(RD_WARPS * 32) k_rowdot_dmma(const uint64_t* __restrict__ conf, const cplx* __restrict__ T,
+        const cplx* __restrict__ v, size_t ns, unsigned N, unsigned M, unsigned words, cplx* __restrict__ a_out) {
+    __shared__ __align__(16) double Vs[RD_KC][RD_CB + RD_PAD];
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u, row = lane >> 2, kq = lane & 3u;
+    const size_t s = (size_t)blockIdx.x * (RD_WARPS * 8) + warp * 8u + row;          // this lane's sample (A row / C row)
+    uint64_t cw[MAXW] = {0ull, 0ull, 0ull, 0ull};
+    #pragma unroll
+    for(unsigned w = 0; w < (unsigned)MAXW; w++) if(s < ns && w < words) cw[w] = conf[s * words + w];
+    const double* __restrict__ vr = reinterpret_cast<const double*>(v);
+    const unsigned ncol = 2u * M;
+    cplx tot(0.0, 0.0);
+    for(unsigned cb = 0; cb < ncol; cb += RD_CB) {
+        double acc[RD_CB / 8][2];
+        #pragma unroll
+        for(int t = 0; t < RD_CB / 8; t++) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+        for(unsigned i0 = 0; i0 < N; i0 += RD_KC) {
+            __syncthreads();
+            for(unsigned e = threadIdx.x; e < RD_KC * RD_CB; e += RD_WARPS * 32) {
+                const unsigned kk = e / RD_CB, c = e % RD_CB;
+                Vs[kk][c] = (i0 + kk < N && cb + c < ncol) ? vr[(size_t)(i0 + kk) * ncol + cb + c] : 0.0;
+            }
+            __syncthreads();
+            #pragma unroll 2
+            for(unsigned k4 = 0; k4 < RD_KC / 4; k4++) {
+                const unsigned i = i0 + k4 * 4u + kq;
+                const unsigned wd = i >> 6;
+                uint64_t word = cw[0];
+                if(wd == 1u) word = cw[1];
+                if(wd == 2u) word = cw[2];
+                if(wd == 3u) word = cw[3];
+                const double asg = (s < ns && i < N) ? (((word >> (i & 63u)) & 1ull) ? 1.0 : -1.0) : 0.0;
+                #pragma unroll
+                for(int t = 0; t < RD_CB / 8; t++) dmma(acc[t][0], acc[t][1], asg, Vs[k4 * 4u + kq][t * 8 + row]);
+            }
+        }
+        if(s < ns) {
+            #pragma unroll
+            for(int t = 0; t < RD_CB / 8; t++) {
+                const unsigned j = (cb >> 1) + (unsigned)t * 4u + kq;
+                if(j < M) cfma(tot, T[s * M + j], cplx(acc[t][0], acc[t][1]));
+            }
+        }
+    }
+    tot.re += __shfl_xor_sync(FULL, tot.re, 1); tot.im += __shfl_xor_sync(FULL, tot.im, 1);
+    tot.re += __shfl_xor_sync(FULL, tot.re, 2); tot.im += __shfl_xor_sync(FULL, tot.im, 2);
+    if(kq == 0 && s < ns) a_out[s] = tot;
+}
+
+constexpr int CD_WARPS = 8, CD_KT = 32, CD_CB = 64, CD_PAD = 8, CD_ITW = 4;   // <= 4 site tiles per warp: N <= 256
+__global__ void __launch_bounds__(CD_WARPS * 32) k_colreduce_dmma(const uint64_t* __restrict__ conf, const cplx* __restrict__ T,
+        const double* __restrict__ w, const cplx* __restrict__ X, size_t ns, unsigned N, unsigned M, unsigned words, size_t chunk,
+        cplx* __restrict__ part_x) {
+    __shared__ __align__(16) double Zs[CD_KT][CD_CB + CD_PAD];
+    __shared__ uint64_t sconf[CD_KT][MAXW];
+    __shared__ cplx swa[CD_KT];
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u, row = lane >> 2, kq = lane & 3u;
+    const unsigned cb = blockIdx.x * CD_CB;                       // first real column of this block
+    const unsigned j0 = cb >> 1;                                  // first complex column
+    const size_t s0 = (size_t)blockIdx.y * chunk, s1 = min(ns, s0 + chunk);
+    const unsigned ntile_i = (N + 7u) / 8u;
+    double acc[CD_ITW][CD_CB / 8][2];
+    #pragma unroll
+    for(int q = 0; q < CD_ITW; q++)
+        #pragma unroll
+        for(int t = 0; t < CD_CB / 8; t++) { acc[q][t][0] = 0.0; acc[q][t][1] = 0.0; }
+    for(size_t sb = s0; sb < s1; sb += CD_KT) {
+        __syncthreads();
+        if(threadIdx.x < CD_KT) {
+            const size_t s = sb + threadIdx.x;
+            swa[threadIdx.x] = (s < s1) ? w[s] * X[s] : cplx(0.0, 0.0);
+            for(unsigned wd = 0; wd < (unsigned)MAXW; wd++) sconf[threadIdx.x][wd] = (s < s1 && wd < words) ? conf[s * words + wd] : 0ull;
+        }
+        __syncthreads();
+        for(unsigned e = threadIdx.x; e < CD_KT * (CD_CB / 2); e += CD_WARPS * 32) {
+            const unsigned st = e / (CD_CB / 2), jj = e % (CD_CB / 2);
+            const size_t s = sb + st;
+            cplx z(0.0, 0.0);
+            if(s < s1 && j0 + jj < M) z = swa[st] * conj(T[s * M + j0 + jj]);
+            Zs[st][2 * jj] = z.re; Zs[st][2 * jj + 1] = z.im;
+        }
+        __syncthreads();
+        #pragma unroll 2
+        for(unsigned k4 = 0; k4 < CD_KT / 4; k4++) {
+            const unsigned st = k4 * 4u + kq;
+            double b[CD_CB / 8];
+            #pragma unroll
+            for(int t = 0; t < CD_CB / 8; t++) b[t] = Zs[st][t * 8 + row];
+            const bool live = sb + st < s1;
+            #pragma unroll
+            for(int q = 0; q < CD_ITW; q++) {
+                const unsigned it = warp + (unsigned)q * CD_WARPS;
+                if(it < ntile_i) {                                 // warp-uniform
+                    const unsigned i = it * 8u + row;
+                    const double asg = (live && i < N) ? bit_sign(sconf[st], i) : 0.0;
+                    #pragma unroll
+                    for(int t = 0; t < CD_CB / 8; t++) dmma(acc[q][t][0], acc[q][t][1], asg, b[t]);
+                }
+            }
+        }
+    }
+    const size_t P = (size_t)N * M;
+    #pragma unroll
+    for(int q = 0; q < CD_ITW; q++) {
+        const unsigned it = warp + (unsigned)q * CD_WARPS;
+        if(it < ntile_i) {
+            const unsigned i = it * 8u + row;
+            #pragma unroll
+            for(int t = 0; t < CD_CB / 8; t++) {
+                const unsigned j = j0 + (unsigned)t * 4u + kq;
+                if(i < N && j < M) part_x[(size_t)blockIdx.y * P + (size_t)i * M + j] = cplx(acc[q][t][0], acc[q][t][1]);
+            }
+        }
+    }
+}
+
 // F_k = F'_k - E conj(Obar_k)      (TDVP.cu.template:300, 331-333)
 __global__ void k_finalize_F(const cplx* __restrict__ packed, unsigned P, cplx* __restrict__ F) {
     const cplx E = packed[0];
@@ -510,6 +640,13 @@ void ExpectationValue::fluctuation(const Operator& op, Psi& psi, Ensemble& ens, 
 
 // ============================================================================================ TDVP
 
+// ANGPU_MATVEC=fma selects the plain-FMA factorised mat-vec kernels (A/B comparison); default: FP64 tensor cores
+static bool use_dmma() {
+    static int v = -1;
+    if(v < 0) { const char* e = getenv("ANGPU_MATVEC"); v = (e && std::string(e) == "fma") ? 0 : 1; }
+    return v == 1;
+}
+
 static unsigned pick_chunks(size_t ns, size_t col_blocks) {
     // enough blocks to fill the GPU twice, chunk >= 32 samples, <= 128 chunks
     const size_t want = ((size_t)ctx().num_sms * 8 + col_blocks - 1) / std::max<size_t>(1, col_blocks);
@@ -535,6 +672,7 @@ static ColPartials col_reduce_partials(TDVP& t, const cplx* X, bool want_mean) {
         t.chunk_buf.resize((size_t)2 * chunks * P);
         cplx* pm = want_mean ? t.chunk_buf.p : nullptr; cplx* px = t.chunk_buf.p + (size_t)chunks * P;
         if(want_mean) k_col_reduce_rbm<true><<<dim3(jb, ib, chunks), 128, 0, stream()>>>(t.S.conf.p, t.T.p, t.S.weight.p, X, ns, t.rbm_N, t.rbm_M, t.words, chunk, pm, px);
+        else if(use_dmma()) k_colreduce_dmma<<<dim3(ceil_div(2 * t.rbm_M, CD_CB), chunks), CD_WARPS * 32, 0, stream()>>>(t.S.conf.p, t.T.p, t.S.weight.p, X, ns, t.rbm_N, t.rbm_M, t.words, chunk, px);
         else k_col_reduce_rbm<false><<<dim3(jb, ib, chunks), 128, 0, stream()>>>(t.S.conf.p, t.T.p, t.S.weight.p, X, ns, t.rbm_N, t.rbm_M, t.words, chunk, pm, px);
         ANGPU_CHECK_LAUNCH(); count_launch();
         return ColPartials{chunks, pm, px};
@@ -649,7 +787,8 @@ void TDVP::matvec(const cplx* v_dev, cplx* out_dev, const cplx* dot_dev, const d
     const size_t ns = S.ns;
     row_a.resize(std::max<size_t>(1, ns));
     if(ns) {
-        if(factorised) k_rowdot_rbm<<<ceil_div(ns, RBM_ST), 256, 0, stream()>>>(S.conf.p, T.p, v_dev, ns, rbm_N, rbm_M, words, row_a.p);
+        if(factorised && use_dmma()) k_rowdot_dmma<<<ceil_div(ns, RD_WARPS * 8), RD_WARPS * 32, 0, stream()>>>(S.conf.p, T.p, v_dev, ns, rbm_N, rbm_M, words, row_a.p);
+        else if(factorised) k_rowdot_rbm<<<ceil_div(ns, RBM_ST), 256, 0, stream()>>>(S.conf.p, T.p, v_dev, ns, rbm_N, rbm_M, words, row_a.p);
         else k_rowdot_dense<<<(unsigned)ns, 256, 0, stream()>>>(O.p, v_dev, P, row_a.p);
         ANGPU_CHECK_LAUNCH(); count_launch();
     }
