@@ -102,8 +102,9 @@ void PsiRBM::upload() {
     for(unsigned i = 0; i < N; i++) for(unsigned j = 0; j < M; j++) t[(size_t)j * N + i] = hW[(size_t)i * M + j];
     dWt.upload(t);
     // rows padded to 32*K complex for the register-resident sampler (rbm_kernels.cuh: k_mc_rbm)
-    if(M <= 512u) {
-        const unsigned Mp = 32u * (M <= 32u ? 1u : M <= 64u ? 2u : M <= 128u ? 4u : M <= 256u ? 8u : 16u);
+    if(M <= 2048u) {
+        const unsigned Mp = (M <= 512u) ? 32u * (M <= 32u ? 1u : M <= 64u ? 2u : M <= 128u ? 4u : M <= 256u ? 8u : 16u)
+                                        : (unsigned)MC_BLOCK_T * ((M + MC_BLOCK_T - 1) / MC_BLOCK_T);
         std::vector<cplx> wp((size_t)N * Mp, cplx(0.0, 0.0));
         for(unsigned i = 0; i < N; i++) for(unsigned j = 0; j < M; j++) wp[(size_t)i * Mp + j] = hW[(size_t)i * M + j];
         dWpad.upload(wp);
@@ -168,10 +169,17 @@ void PsiRBM::ok_rows(SampleSet& S, size_t s0, size_t cnt, cplx* out) {
 template<int K, int WORDS>
 static void launch_mc_rbm(const RbmDev& d, const cplx* Wp, const McParams& mc, SampleSet& S, unsigned long long* acc_rej_dev) {
     const unsigned wpb = MC_RBM_THREADS / 32, grid = ceil_div(mc.num_chains_local, wpb);
-    if(d.fw.im == 0.0)
-        k_mc_rbm<K, WORDS, true><<<grid, wpb * 32, 0, stream()>>>(d, Wp, mc, S.conf.p, S.log_psi.p, S.angles.p, acc_rej_dev);
+    // resident blocks per SM requested from ptxas: 8 (<= 128 registers) by default; ANGPU_MC_MINB=10 trades a few spills
+    // for 20 warps per SM (experiment knob, K = 8 with one-word configurations only)
+    static const int minb = [] { const char* e = getenv("ANGPU_MC_MINB"); return e ? atoi(e) : 8; }();
+    constexpr int DEF = (K <= 8) ? 8 : 1;
+    if(K == 8 && WORDS == 1 && minb == 10) {
+        if(d.fw.im == 0.0) k_mc_rbm<K, WORDS, true, (K == 8 && WORDS == 1) ? 10 : DEF><<<grid, wpb * 32, 0, stream()>>>(d, Wp, mc, S.conf.p, S.log_psi.p, S.angles.p, acc_rej_dev);
+        else k_mc_rbm<K, WORDS, false, (K == 8 && WORDS == 1) ? 10 : DEF><<<grid, wpb * 32, 0, stream()>>>(d, Wp, mc, S.conf.p, S.log_psi.p, S.angles.p, acc_rej_dev);
+    } else if(d.fw.im == 0.0)
+        k_mc_rbm<K, WORDS, true, DEF><<<grid, wpb * 32, 0, stream()>>>(d, Wp, mc, S.conf.p, S.log_psi.p, S.angles.p, acc_rej_dev);
     else
-        k_mc_rbm<K, WORDS, false><<<grid, wpb * 32, 0, stream()>>>(d, Wp, mc, S.conf.p, S.log_psi.p, S.angles.p, acc_rej_dev);
+        k_mc_rbm<K, WORDS, false, DEF><<<grid, wpb * 32, 0, stream()>>>(d, Wp, mc, S.conf.p, S.log_psi.p, S.angles.p, acc_rej_dev);
     ANGPU_CHECK_LAUNCH(); count_launch();
 }
 template<int K>
@@ -197,6 +205,23 @@ void PsiRBM::mc_sample(const McParams& mc, SampleSet& S, unsigned long long* acc
             case 8: launch_mc_rbm_k<8>(d, dWpad.p, mc, S, acc_rej_dev); break;
             default: launch_mc_rbm_k<16>(d, dWpad.p, mc, S, acc_rej_dev); break;
         }
+        S.has_angles = true;
+    } else if(M <= 2048u) {
+        S.angles.resize(S.ns * M);
+        const unsigned K = (M + MC_BLOCK_T - 1) / MC_BLOCK_T;          // 3..8
+        auto launch = [&](auto kr, auto kc) {
+            if(d.fw.im == 0.0) kr<<<mc.num_chains_local, MC_BLOCK_T, 0, stream()>>>(d, dWpad.p, mc, S.conf.p, S.log_psi.p, S.angles.p, acc_rej_dev);
+            else kc<<<mc.num_chains_local, MC_BLOCK_T, 0, stream()>>>(d, dWpad.p, mc, S.conf.p, S.log_psi.p, S.angles.p, acc_rej_dev);
+        };
+        switch(K) {
+            case 3: launch(k_mc_rbm_block<3, true>, k_mc_rbm_block<3, false>); break;
+            case 4: launch(k_mc_rbm_block<4, true>, k_mc_rbm_block<4, false>); break;
+            case 5: launch(k_mc_rbm_block<5, true>, k_mc_rbm_block<5, false>); break;
+            case 6: launch(k_mc_rbm_block<6, true>, k_mc_rbm_block<6, false>); break;
+            case 7: launch(k_mc_rbm_block<7, true>, k_mc_rbm_block<7, false>); break;
+            default: launch(k_mc_rbm_block<8, true>, k_mc_rbm_block<8, false>); break;
+        }
+        ANGPU_CHECK_LAUNCH(); count_launch();
         S.has_angles = true;
     } else {
         generic_mc(d, mc, S, acc_rej_dev);

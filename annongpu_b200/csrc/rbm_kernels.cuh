@@ -122,8 +122,8 @@ __device__ __forceinline__ void conf_flip_t(uint64_t (&c)[MAXW], unsigned site) 
 
 // Wp: W with rows padded to Mp = 32*K complex (zeros beyond M) so that the hot loop has no bounds checks and one
 // base address per proposal: lane l reads Wp[site][l + 32k], k < K (coalesced 512 B per k).
-template<int K, int WORDS, bool FW_REAL>
-__global__ void __launch_bounds__(MC_RBM_THREADS, (K <= 8) ? MC_RBM_MINB : 1)
+template<int K, int WORDS, bool FW_REAL, int MINB>
+__global__ void __launch_bounds__(MC_RBM_THREADS, MINB)
 k_mc_rbm(const RbmDev psi, const cplx* __restrict__ Wp, const McParams mc, uint64_t* __restrict__ conf_out,
          cplx* __restrict__ log_psi_out, cplx* __restrict__ angles_out, unsigned long long* __restrict__ acc_rej) {
     constexpr unsigned Mp = 32u * K;
@@ -221,6 +221,128 @@ k_mc_rbm(const RbmDev psi, const cplx* __restrict__ Wp, const McParams mc, uint6
         }
     }
     if(lane == 0) { atomicAdd(&acc_rej[0], acc); atomicAdd(&acc_rej[1], total_steps - acc); }
+}
+
+// Block-per-chain variant for wide RBMs (512 < M <= 2048, e.g. BASELINE C5: M = 1600): the angles still live in
+// registers, K = ceil(M/256) per thread of a 256-thread block; one __syncthreads per proposal (the 8 warp partial sums
+// are exchanged through a double-buffered shared-memory slot and every thread adds them in the same order, so the
+// accept/reject decision is uniform without a second barrier).  Wp rows are padded to 256*K.
+constexpr int MC_BLOCK_T = 256;
+template<int K, bool FW_REAL>
+__global__ void __launch_bounds__(MC_BLOCK_T, 2)
+k_mc_rbm_block(const RbmDev psi, const cplx* __restrict__ Wp, const McParams mc, uint64_t* __restrict__ conf_out,
+               cplx* __restrict__ log_psi_out, cplx* __restrict__ angles_out, unsigned long long* __restrict__ acc_rej) {
+    constexpr unsigned Mp = (unsigned)MC_BLOCK_T * K;
+    __shared__ cplx part[2][MC_BLOCK_T / 32];
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const unsigned chain = blockIdx.x;
+    const unsigned gchain = mc.chain0 + chain;
+    const unsigned M = psi.M, N = psi.N;
+    const unsigned tag_init = (mc.call << 1) | 0u, tag_step = (mc.call << 1) | 1u;
+    const cplx* __restrict__ Wl = Wp + tid;
+
+    uint32_t r[4];
+    uint64_t conf[MAXW] = {0ull, 0ull, 0ull, 0ull};
+    #pragma unroll
+    for(unsigned w = 0; w < (unsigned)MAXW; w++) {
+        if(w < psi.words) {
+            philox4x32_10(w, 0u, gchain, tag_init, mc.seed_lo, mc.seed_hi, r);
+            conf[w] = (uint64_t)r[0] | ((uint64_t)r[1] << 32);
+            if(w == psi.words - 1u && (N & 63u)) conf[w] &= (1ull << (N & 63u)) - 1ull;
+        }
+    }
+    cplx th[K];
+    #pragma unroll
+    for(int k = 0; k < K; k++) th[k] = cplx(0.0, 0.0);
+    for(unsigned i = 0; i < N; i++) {
+        const double s = conf_spin(conf, i);
+        #pragma unroll
+        for(int k = 0; k < K; k++) th[k] += s * ldg(&Wl[(size_t)i * Mp + (unsigned)MC_BLOCK_T * k]);
+    }
+    unsigned buf = 0;
+    // block-wide sum of one complex per thread, identical on every thread (fixed order), ONE barrier
+    auto block_sum = [&](cplx v) -> cplx {
+        v = warp_sum(v);
+        if(lane == 0) part[buf][warp] = v;
+        __syncthreads();
+        cplx t(0.0, 0.0);
+        #pragma unroll
+        for(int q = 0; q < MC_BLOCK_T / 32; q++) t += part[buf][q];
+        buf ^= 1u;
+        return t;
+    };
+    auto re_log_psi = [&]() -> double {
+        cplx p(0.0, 0.0);
+        if(FW_REAL) {
+            #pragma unroll
+            for(int k = 0; k < K; k++) p.re += lc0_re_pq(th[k].re, th[k].im);
+        } else {
+            #pragma unroll
+            for(int k = 0; k < K; k++) p += lc0_pq(th[k].re, th[k].im);
+        }
+        p = block_sum(p);
+        return psi.lp.re + psi.fw.re * p.re - psi.fw.im * p.im;
+    };
+    double cur_re = re_log_psi();
+
+    const unsigned therm = mc.num_therm * N, per_sample = mc.num_sweeps * N;
+    const unsigned long long total_steps = (unsigned long long)therm + (unsigned long long)per_sample * mc.steps_per_chain;
+    unsigned long long acc = 0;
+    unsigned long long next_record = (unsigned long long)therm + per_sample;
+    unsigned sample = 0;
+
+    for(unsigned long long t0 = 0; t0 < total_steps; t0 += 32u) {
+        philox4x32_10((uint32_t)(t0 + lane), (uint32_t)((t0 + lane) >> 32), gchain, tag_step, mc.seed_lo, mc.seed_hi, r);
+        const unsigned my_site = r[0] % N;
+        const unsigned my_ulo = r[1], my_uhi = r[2];
+        const unsigned nb = (unsigned)min((unsigned long long)32u, total_steps - t0);
+        // the W row of the first proposal of this batch
+        cplx wn[K];
+        {
+            const unsigned site0 = __shfl_sync(FULL, my_site, 0);
+            #pragma unroll
+            for(int k = 0; k < K; k++) wn[k] = ldg(&Wl[(size_t)site0 * Mp + (unsigned)MC_BLOCK_T * k]);
+        }
+        for(unsigned b = 0; b < nb; b++) {
+            const unsigned site = __shfl_sync(FULL, my_site, b);
+            const double u = u01_from_bits(__shfl_sync(FULL, my_ulo, b), __shfl_sync(FULL, my_uhi, b));
+            const double delta = -2.0 * conf_spin(conf, site);
+            cplx w[K];
+            #pragma unroll
+            for(int k = 0; k < K; k++) { w[k] = wn[k]; th[k].re = fma(delta, w[k].re, th[k].re); th[k].im = fma(delta, w[k].im, th[k].im); }
+            if(b + 1u < nb) {                                   // prefetch the next proposal's row (L2 latency)
+                const unsigned site_n = __shfl_sync(FULL, my_site, b + 1u);
+                #pragma unroll
+                for(int k = 0; k < K; k++) wn[k] = ldg(&Wl[(size_t)site_n * Mp + (unsigned)MC_BLOCK_T * k]);
+            }
+            const double new_re = re_log_psi();
+            if(metropolis_accept(2.0 * (new_re - cur_re), u)) {
+                cur_re = new_re;
+                conf_flip(conf, site);
+                acc++;
+            } else {
+                #pragma unroll
+                for(int k = 0; k < K; k++) { th[k].re = fma(-delta, w[k].re, th[k].re); th[k].im = fma(-delta, w[k].im, th[k].im); }
+            }
+            if(t0 + b + 1u == next_record) {
+                const size_t idx = (size_t)sample * mc.num_chains_local + chain;
+                cplx p(0.0, 0.0);
+                #pragma unroll
+                for(int k = 0; k < K; k++) {
+                    const unsigned j = tid + (unsigned)MC_BLOCK_T * k;
+                    if(j < M) { p += lc0(th[k]); if(angles_out) angles_out[idx * M + j] = th[k]; }
+                }
+                p = block_sum(p);
+                if(tid == 0) {
+                    log_psi_out[idx] = psi.lp + psi.fw * p;
+                    #pragma unroll
+                    for(unsigned ww = 0; ww < (unsigned)MAXW; ww++) if(ww < psi.words) conf_out[idx * psi.words + ww] = conf[ww];
+                }
+                sample++; next_record += per_sample;
+            }
+        }
+    }
+    if(tid == 0) { atomicAdd(&acc_rej[0], acc); atomicAdd(&acc_rej[1], total_steps - acc); }
 }
 
 // theta = W^T s and log psi for given configurations (ExactSummation / probes); one warp per configuration.

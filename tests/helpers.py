@@ -73,6 +73,11 @@ def zoo():
     return z
 
 
+def wide_zoo():
+    """Shapes beyond the reference's compiled-in limits (M > 128): checked against the port only."""
+    return {"rbm_wide": (F.rbm_spec(12, 600, noise=2e-2, final_weight=0.5, seed=13), F.heisenberg(12, F.ring_bonds(12)), 12)}
+
+
 def classical_zoo():
     N = 6
     Hl = [F.PauliSum(N).add(1.0, {i: "Z", (i + 1) % N: "Z"}).add(0.3, {i: "X"}).add(0.2j, {i: "Y", (i + 2) % N: "Z"}) for i in range(N)]

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from annongpu_b200 import factories as F
-from helpers import classical_zoo, make_classical, make_op, make_psi, rel_err, zoo
+from helpers import classical_zoo, make_classical, make_op, make_psi, rel_err, wide_zoo, zoo
 
 pytestmark = pytest.mark.gpu
 
@@ -176,10 +176,10 @@ def test_expectation_list_and_hermitian_identity(gpu, port):
 
 # ------------------------------------------------------------------------------------------------ Monte Carlo
 
-@pytest.mark.parametrize("name", ["rbm10", "rbm8_cfw", "rbm12_m40", "deep2", "cnn"])
+@pytest.mark.parametrize("name", ["rbm10", "rbm8_cfw", "rbm12_m40", "rbm_wide", "deep2", "cnn"])
 def test_mc_chains_identical_to_oracle(gpu, port, name):
     """Same Philox stream, same proposals: the sampled configurations must coincide chain by chain."""
-    spec, H, N = zoo()[name]
+    spec, H, N = {**zoo(), **wide_zoo()}[name]
     pg, pp = make_psi(gpu, spec), make_psi(port, spec)
     chains, per_chain = 24, 3
     mg = gpu.MonteCarloSpins(chains * per_chain, 2, 3, chains, True, seed=1234)
