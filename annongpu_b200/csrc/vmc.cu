@@ -265,10 +265,22 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 }
 __device__ __forceinline__ double bit_sign(const uint64_t* cw, unsigned i) { return ((cw[i >> 6] >> (i & 63u)) & 1ull) ? 1.0 : -1.0; }
 
-constexpr int RD_WARPS = 4, RD_KC = 32, RD_CB = 128, RD_PAD = 8;      // 32 samples per block, 128 real columns per pass
+constexpr int RD_WARPS = 8, RD_KC = 32, RD_CB = 128, RD_PAD = 8;      // 64 samples per block, 128 real columns per pass
+constexpr int RD_STRIDE = RD_CB + RD_PAD;
+constexpr int RD_STAGE_DOUBLES = RD_KC * RD_STRIDE;
+constexpr size_t RD_SMEM = 2 * RD_STAGE_DOUBLES * sizeof(double);       // double-buffered V tile (cp.async)
+
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool valid) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int bytes = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template<int N_> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+
 __global__ void __launch_bounds__(RD_WARPS * 32) k_rowdot_dmma(const uint64_t* __restrict__ conf, const cplx* __restrict__ T,
         const cplx* __restrict__ v, size_t ns, unsigned N, unsigned M, unsigned words, cplx* __restrict__ a_out) {
-    __shared__ __align__(16) double Vs[RD_KC][RD_CB + RD_PAD];
+    extern __shared__ __align__(16) double rd_smem[];
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u, row = lane >> 2, kq = lane & 3u;
     const size_t s = (size_t)blockIdx.x * (RD_WARPS * 8) + warp * 8u + row;          // this lane's sample (A row / C row)
     uint64_t cw[MAXW] = {0ull, 0ull, 0ull, 0ull};
@@ -276,77 +288,106 @@ __global__ void __launch_bounds__(RD_WARPS * 32) k_rowdot_dmma(const uint64_t* _
     for(unsigned w = 0; w < (unsigned)MAXW; w++) if(s < ns && w < words) cw[w] = conf[s * words + w];
     const double* __restrict__ vr = reinterpret_cast<const double*>(v);
     const unsigned ncol = 2u * M;
+    const unsigned nkc = (N + RD_KC - 1) / RD_KC, ncb = (ncol + RD_CB - 1) / RD_CB, nstage = nkc * ncb;
+    // stage q = (column block q / nkc, site chunk q % nkc): 32 sites x 128 doubles, 16-byte cp.async chunks, zero-filled OOB
+    auto issue = [&](unsigned q) {
+        double* dst = rd_smem + (q & 1u) * RD_STAGE_DOUBLES;
+        const unsigned cb = (q / nkc) * RD_CB, i0 = (q % nkc) * RD_KC;
+        for(unsigned e = threadIdx.x; e < RD_KC * (RD_CB / 2); e += RD_WARPS * 32) {
+            const unsigned kk = e / (RD_CB / 2), c = (e % (RD_CB / 2)) * 2u;
+            const bool ok = (i0 + kk < N) && (cb + c < ncol);
+            cp_async16_zfill(dst + kk * RD_STRIDE + c, ok ? (const void*)(vr + (size_t)(i0 + kk) * ncol + cb + c) : (const void*)vr, ok);
+        }
+        cp_async_commit();
+    };
     cplx tot(0.0, 0.0);
-    for(unsigned cb = 0; cb < ncol; cb += RD_CB) {
-        double acc[RD_CB / 8][2];
-        #pragma unroll
-        for(int t = 0; t < RD_CB / 8; t++) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
-        for(unsigned i0 = 0; i0 < N; i0 += RD_KC) {
-            __syncthreads();
-            for(unsigned e = threadIdx.x; e < RD_KC * RD_CB; e += RD_WARPS * 32) {
-                const unsigned kk = e / RD_CB, c = e % RD_CB;
-                Vs[kk][c] = (i0 + kk < N && cb + c < ncol) ? vr[(size_t)(i0 + kk) * ncol + cb + c] : 0.0;
-            }
-            __syncthreads();
-            #pragma unroll 2
-            for(unsigned k4 = 0; k4 < RD_KC / 4; k4++) {
-                const unsigned i = i0 + k4 * 4u + kq;
-                const unsigned wd = i >> 6;
-                uint64_t word = cw[0];
-                if(wd == 1u) word = cw[1];
-                if(wd == 2u) word = cw[2];
-                if(wd == 3u) word = cw[3];
-                const double asg = (s < ns && i < N) ? (((word >> (i & 63u)) & 1ull) ? 1.0 : -1.0) : 0.0;
-                #pragma unroll
-                for(int t = 0; t < RD_CB / 8; t++) dmma(acc[t][0], acc[t][1], asg, Vs[k4 * 4u + kq][t * 8 + row]);
-            }
-        }
-        if(s < ns) {
+    double acc[RD_CB / 8][2];
+    #pragma unroll
+    for(int t = 0; t < RD_CB / 8; t++) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+    issue(0);
+    for(unsigned q = 0; q < nstage; q++) {
+        if(q + 1u < nstage) { issue(q + 1u); cp_async_wait<1>(); } else cp_async_wait<0>();
+        __syncthreads();
+        const double* Vs = rd_smem + (q & 1u) * RD_STAGE_DOUBLES;
+        const unsigned cb = (q / nkc) * RD_CB, i0 = (q % nkc) * RD_KC;
+        #pragma unroll 2
+        for(unsigned k4 = 0; k4 < RD_KC / 4; k4++) {
+            const unsigned i = i0 + k4 * 4u + kq;
+            const unsigned wd = i >> 6;
+            uint64_t word = cw[0];
+            if(wd == 1u) word = cw[1];
+            if(wd == 2u) word = cw[2];
+            if(wd == 3u) word = cw[3];
+            const double asg = (s < ns && i < N) ? (((word >> (i & 63u)) & 1ull) ? 1.0 : -1.0) : 0.0;
+            const double* vrow = Vs + (k4 * 4u + kq) * RD_STRIDE + row;
             #pragma unroll
-            for(int t = 0; t < RD_CB / 8; t++) {
-                const unsigned j = (cb >> 1) + (unsigned)t * 4u + kq;
-                if(j < M) cfma(tot, T[s * M + j], cplx(acc[t][0], acc[t][1]));
-            }
+            for(int t = 0; t < RD_CB / 8; t++) dmma(acc[t][0], acc[t][1], asg, vrow[t * 8]);
         }
+        if(q % nkc == nkc - 1u) {                          // column block complete: a_s += sum_j T_sj U_sj, reset
+            if(s < ns) {
+                #pragma unroll
+                for(int t = 0; t < RD_CB / 8; t++) {
+                    const unsigned j = (cb >> 1) + (unsigned)t * 4u + kq;
+                    if(j < M) cfma(tot, T[s * M + j], cplx(acc[t][0], acc[t][1]));
+                }
+            }
+            #pragma unroll
+            for(int t = 0; t < RD_CB / 8; t++) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+        }
+        __syncthreads();                                   // the buffer is refilled by the next iteration's issue
     }
     tot.re += __shfl_xor_sync(FULL, tot.re, 1); tot.im += __shfl_xor_sync(FULL, tot.im, 1);
     tot.re += __shfl_xor_sync(FULL, tot.re, 2); tot.im += __shfl_xor_sync(FULL, tot.im, 2);
     if(kq == 0 && s < ns) a_out[s] = tot;
 }
 
-constexpr int CD_WARPS = 8, CD_KT = 32, CD_CB = 64, CD_PAD = 8, CD_ITW = 4;   // <= 4 site tiles per warp: N <= 256
+constexpr int CD_WARPS = 8, CD_KT = 32, CD_PAD = 8;   // tiles of 32 samples x CD_CB real columns
+template<int ITW, int CD_CB>                            // ITW site tiles (of 8) per warp: N <= 64 * ITW; CD_CB in {64, 128}
 __global__ void __launch_bounds__(CD_WARPS * 32) k_colreduce_dmma(const uint64_t* __restrict__ conf, const cplx* __restrict__ T,
         const double* __restrict__ w, const cplx* __restrict__ X, size_t ns, unsigned N, unsigned M, unsigned words, size_t chunk,
         cplx* __restrict__ part_x) {
     __shared__ __align__(16) double Zs[CD_KT][CD_CB + CD_PAD];
     __shared__ uint64_t sconf[CD_KT][MAXW];
-    __shared__ cplx swa[CD_KT];
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u, row = lane >> 2, kq = lane & 3u;
     const unsigned cb = blockIdx.x * CD_CB;                       // first real column of this block
     const unsigned j0 = cb >> 1;                                  // first complex column
     const size_t s0 = (size_t)blockIdx.y * chunk, s1 = min(ns, s0 + chunk);
     const unsigned ntile_i = (N + 7u) / 8u;
-    double acc[CD_ITW][CD_CB / 8][2];
+    double acc[ITW][CD_CB / 8][2];
     #pragma unroll
-    for(int q = 0; q < CD_ITW; q++)
+    for(int q = 0; q < ITW; q++)
         #pragma unroll
         for(int t = 0; t < CD_CB / 8; t++) { acc[q][t][0] = 0.0; acc[q][t][1] = 0.0; }
-    for(size_t sb = s0; sb < s1; sb += CD_KT) {
-        __syncthreads();
-        if(threadIdx.x < CD_KT) {
-            const size_t s = sb + threadIdx.x;
-            swa[threadIdx.x] = (s < s1) ? w[s] * X[s] : cplx(0.0, 0.0);
-            for(unsigned wd = 0; wd < (unsigned)MAXW; wd++) sconf[threadIdx.x][wd] = (s < s1 && wd < words) ? conf[s * words + wd] : 0ull;
-        }
-        __syncthreads();
-        for(unsigned e = threadIdx.x; e < CD_KT * (CD_CB / 2); e += CD_WARPS * 32) {
+    // register prefetch of the next tile's z = w a conj(T): element e = threadIdx.x + 256 m -> (sample e / 64, column e % 64)
+    constexpr int CD_ZPT = CD_KT * (CD_CB / 2) / (CD_WARPS * 32);      // z elements staged per thread
+    cplx zreg[CD_ZPT];
+    auto fetch = [&](size_t sb) {
+        #pragma unroll
+        for(int m = 0; m < CD_ZPT; m++) {
+            const unsigned e = threadIdx.x + (unsigned)m * (CD_WARPS * 32);
             const unsigned st = e / (CD_CB / 2), jj = e % (CD_CB / 2);
-            const size_t s = sb + st;
+            const size_t sidx = sb + st;
             cplx z(0.0, 0.0);
-            if(s < s1 && j0 + jj < M) z = swa[st] * conj(T[s * M + j0 + jj]);
-            Zs[st][2 * jj] = z.re; Zs[st][2 * jj + 1] = z.im;
+            if(sidx < s1 && j0 + jj < M) z = (w[sidx] * X[sidx]) * conj(T[sidx * M + j0 + jj]);
+            zreg[m] = z;
+        }
+    };
+    if(s0 < s1) fetch(s0);
+    for(size_t sb = s0; sb < s1; sb += CD_KT) {
+        __syncthreads();                                          // previous tile fully consumed
+        #pragma unroll
+        for(int m = 0; m < CD_ZPT; m++) {
+            const unsigned e = threadIdx.x + (unsigned)m * (CD_WARPS * 32);
+            const unsigned st = e / (CD_CB / 2), jj = e % (CD_CB / 2);
+            *reinterpret_cast<double2*>(&Zs[st][2 * jj]) = make_double2(zreg[m].re, zreg[m].im);
+        }
+        if(threadIdx.x < CD_KT * MAXW) {
+            const unsigned st = threadIdx.x / MAXW, wd = threadIdx.x % MAXW;
+            const size_t sidx = sb + st;
+            sconf[st][wd] = (sidx < s1 && wd < words) ? conf[sidx * words + wd] : 0ull;
         }
         __syncthreads();
+        if(sb + CD_KT < s1) fetch(sb + CD_KT);                    // overlaps the global latency with the MMAs below
         #pragma unroll 2
         for(unsigned k4 = 0; k4 < CD_KT / 4; k4++) {
             const unsigned st = k4 * 4u + kq;
@@ -355,7 +396,7 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_colreduce_dmma(const uint64_t
             for(int t = 0; t < CD_CB / 8; t++) b[t] = Zs[st][t * 8 + row];
             const bool live = sb + st < s1;
             #pragma unroll
-            for(int q = 0; q < CD_ITW; q++) {
+            for(int q = 0; q < ITW; q++) {
                 const unsigned it = warp + (unsigned)q * CD_WARPS;
                 if(it < ntile_i) {                                 // warp-uniform
                     const unsigned i = it * 8u + row;
@@ -368,7 +409,7 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_colreduce_dmma(const uint64_t
     }
     const size_t P = (size_t)N * M;
     #pragma unroll
-    for(int q = 0; q < CD_ITW; q++) {
+    for(int q = 0; q < ITW; q++) {
         const unsigned it = warp + (unsigned)q * CD_WARPS;
         if(it < ntile_i) {
             const unsigned i = it * 8u + row;
@@ -507,6 +548,70 @@ __global__ void __launch_bounds__(RED_T) k_cg_fused(cplx* __restrict__ x, cplx* 
     }
     block_reduce<2>(v, red);
     if(threadIdx.x == 0) { scal[0] = scal[2]; scal[3] = cplx(red[0], red[1]); }
+}
+
+// ============================================================================================ multi-block CG vector kernels
+// (n > 64k, e.g. C5 with P = 320000): per-block partial sums in a fixed number of blocks, summed by every consumer in
+// the same order (deterministic, no atomics).  scal: [0] rs, [1] pAp, [2] rs_new.
+constexpr int VB_BLOCKS = 148, VB_T = 256;
+template<int NV>
+__device__ void block_reduce_small(double (&v)[NV], double* out) {      // VB_T threads
+    __shared__ double sm[NV][VB_T / 32];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    #pragma unroll
+    for(int i = 0; i < NV; i++) { v[i] = warp_sum(v[i]); if(lane == 0) sm[i][warp] = v[i]; }
+    __syncthreads();
+    if(warp == 0) {
+        #pragma unroll
+        for(int i = 0; i < NV; i++) {
+            double x = (lane < VB_T / 32) ? sm[i][lane] : 0.0;
+            x = warp_sum(x);
+            if(lane == 0) out[i] = x;
+        }
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ cplx sum_partials(const cplx* part) {
+    cplx t(0.0, 0.0);
+    for(int b = 0; b < VB_BLOCKS; b++) t += part[b];
+    return t;
+}
+// part[b] = sum over the block's elements of op(a) b
+template<bool CONJ_A>
+__global__ void __launch_bounds__(VB_T) k_dot_part(const cplx* __restrict__ a, const cplx* __restrict__ b, size_t n, cplx* __restrict__ part,
+                                                   cplx* scal_roll) {
+    if(scal_roll && blockIdx.x == 0 && threadIdx.x == 0) scal_roll[0] = scal_roll[2];        // rs <- rs_new of the last iteration
+    double v[2] = {0, 0}, r[2];
+    for(size_t k = (size_t)blockIdx.x * VB_T + threadIdx.x; k < n; k += (size_t)VB_BLOCKS * VB_T) {
+        cplx x = a[k]; if(CONJ_A) x = conj(x);
+        const cplx p = x * b[k];
+        v[0] += p.re; v[1] += p.im;
+    }
+    block_reduce_small<2>(v, r);
+    if(threadIdx.x == 0) part[blockIdx.x] = cplx(r[0], r[1]);
+}
+__global__ void k_sum_part_to_scalar(const cplx* __restrict__ part, cplx* out) { if(threadIdx.x == 0) *out = sum_partials(part); }
+// alpha = rs / sum(part_pAp); x += alpha p; r -= alpha Ap; part_rr[b] = sum |r|^2
+__global__ void __launch_bounds__(VB_T) k_cg_xr_mb(cplx* __restrict__ x, cplx* __restrict__ r, const cplx* __restrict__ p, const cplx* __restrict__ Ap,
+                                                   const cplx* __restrict__ scal, const cplx* __restrict__ part_pAp, cplx* __restrict__ part_rr, size_t n) {
+    const double alpha = scal[0].re / sum_partials(part_pAp).re;
+    double v[1] = {0}, red[1];
+    for(size_t k = (size_t)blockIdx.x * VB_T + threadIdx.x; k < n; k += (size_t)VB_BLOCKS * VB_T) {
+        x[k] += alpha * p[k];
+        const cplx rk = r[k] - alpha * Ap[k];
+        r[k] = rk;
+        v[0] += abs2(rk);
+    }
+    block_reduce_small<1>(v, red);
+    if(threadIdx.x == 0) part_rr[blockIdx.x] = cplx(red[0], 0.0);
+}
+// rs_new = sum(part_rr); beta = rs_new / rs; p = r + beta p; scal[2] = rs_new
+__global__ void __launch_bounds__(VB_T) k_cg_p_mb(cplx* __restrict__ p, const cplx* __restrict__ r, cplx* __restrict__ scal,
+                                                  const cplx* __restrict__ part_rr, size_t n) {
+    const double rs_new = sum_partials(part_rr).re;
+    const double beta = rs_new / scal[0].re;
+    for(size_t k = (size_t)blockIdx.x * VB_T + threadIdx.x; k < n; k += (size_t)VB_BLOCKS * VB_T) p[k] = r[k] + beta * p[k];
+    if(blockIdx.x == 0 && threadIdx.x == 0) scal[2] = cplx(rs_new, 0.0);
 }
 
 // ============================================================================================ solver kernels
@@ -666,13 +771,23 @@ static ColPartials col_reduce_partials(TDVP& t, const cplx* X, bool want_mean) {
     unsigned chunks; size_t chunk;
     if(t.factorised) {
         const unsigned jb = ceil_div(t.rbm_M, 128), ib = ceil_div(t.rbm_N, RBM_IT);
-        // chunks of whole 32-sample tiles; <= 64 chunks keeps the partial-sum traffic (chunks*P*16 B) small
-        chunks = (unsigned)std::max<size_t>(1, std::min<size_t>(64, (ns + RBM_TS - 1) / RBM_TS));
+        // chunks of whole 32-sample tiles: enough blocks to fill the GPU twice, but the partial-sum traffic
+        // (chunks * P * 16 B written and read back) is kept below ~64 MB and chunks <= 64
+        const size_t colblocks = (2 * (size_t)t.rbm_M + 127) / 128;
+        size_t want_chunks = ((size_t)ctx().num_sms * 2 + colblocks - 1) / colblocks;
+        want_chunks = std::min<size_t>(want_chunks, std::max<size_t>(1, ((size_t)64 << 20) / ((size_t)P * sizeof(cplx))));
+        if(want_mean) want_chunks = 64;
+        chunks = (unsigned)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(64, want_chunks), (ns + RBM_TS - 1) / RBM_TS));
         chunk = ((ns + chunks - 1) / chunks + RBM_TS - 1) / RBM_TS * RBM_TS; chunks = (unsigned)((ns + chunk - 1) / chunk);
         t.chunk_buf.resize((size_t)2 * chunks * P);
         cplx* pm = want_mean ? t.chunk_buf.p : nullptr; cplx* px = t.chunk_buf.p + (size_t)chunks * P;
         if(want_mean) k_col_reduce_rbm<true><<<dim3(jb, ib, chunks), 128, 0, stream()>>>(t.S.conf.p, t.T.p, t.S.weight.p, X, ns, t.rbm_N, t.rbm_M, t.words, chunk, pm, px);
-        else if(use_dmma()) k_colreduce_dmma<<<dim3(ceil_div(2 * t.rbm_M, CD_CB), chunks), CD_WARPS * 32, 0, stream()>>>(t.S.conf.p, t.T.p, t.S.weight.p, X, ns, t.rbm_N, t.rbm_M, t.words, chunk, px);
+        else if(use_dmma()) {
+            const dim3 g128(ceil_div(2 * t.rbm_M, 128), chunks), g64(ceil_div(2 * t.rbm_M, 64), chunks);
+            if(t.rbm_N <= 64u) k_colreduce_dmma<1, 128><<<g128, CD_WARPS * 32, 0, stream()>>>(t.S.conf.p, t.T.p, t.S.weight.p, X, ns, t.rbm_N, t.rbm_M, t.words, chunk, px);
+            else if(t.rbm_N <= 128u) k_colreduce_dmma<2, 64><<<g64, CD_WARPS * 32, 0, stream()>>>(t.S.conf.p, t.T.p, t.S.weight.p, X, ns, t.rbm_N, t.rbm_M, t.words, chunk, px);
+            else k_colreduce_dmma<4, 64><<<g64, CD_WARPS * 32, 0, stream()>>>(t.S.conf.p, t.T.p, t.S.weight.p, X, ns, t.rbm_N, t.rbm_M, t.words, chunk, px);
+        }
         else k_col_reduce_rbm<false><<<dim3(jb, ib, chunks), 128, 0, stream()>>>(t.S.conf.p, t.T.p, t.S.weight.p, X, ns, t.rbm_N, t.rbm_M, t.words, chunk, pm, px);
         ANGPU_CHECK_LAUNCH(); count_launch();
         return ColPartials{chunks, pm, px};
@@ -787,7 +902,11 @@ void TDVP::matvec(const cplx* v_dev, cplx* out_dev, const cplx* dot_dev, const d
     const size_t ns = S.ns;
     row_a.resize(std::max<size_t>(1, ns));
     if(ns) {
-        if(factorised && use_dmma()) k_rowdot_dmma<<<ceil_div(ns, RD_WARPS * 8), RD_WARPS * 32, 0, stream()>>>(S.conf.p, T.p, v_dev, ns, rbm_N, rbm_M, words, row_a.p);
+        if(factorised && use_dmma()) {
+            static bool attr_set = false;
+            if(!attr_set) { ANGPU_CUDA(cudaFuncSetAttribute(k_rowdot_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RD_SMEM)); attr_set = true; }
+            k_rowdot_dmma<<<ceil_div(ns, RD_WARPS * 8), RD_WARPS * 32, RD_SMEM, stream()>>>(S.conf.p, T.p, v_dev, ns, rbm_N, rbm_M, words, row_a.p);
+        }
         else if(factorised) k_rowdot_rbm<<<ceil_div(ns, RBM_ST), 256, 0, stream()>>>(S.conf.p, T.p, v_dev, ns, rbm_N, rbm_M, words, row_a.p);
         else k_rowdot_dense<<<(unsigned)ns, 256, 0, stream()>>>(O.p, v_dev, P, row_a.p);
         ANGPU_CHECK_LAUNCH(); count_launch();
@@ -795,7 +914,12 @@ void TDVP::matvec(const cplx* v_dev, cplx* out_dev, const cplx* dot_dev, const d
     d_scal.resize(16);
     if(!dot_dev) {
         cplx* dot = reinterpret_cast<cplx*>(d_scal.p) + 4;
-        k_dot<false><<<1, RED_T, 0, stream()>>>(Ok_dev(), v_dev, P, dot);
+        if(P > 65536u) {
+            vb_part.resize(3 * VB_BLOCKS);
+            k_dot_part<false><<<VB_BLOCKS, VB_T, 0, stream()>>>(Ok_dev(), v_dev, P, vb_part.p + 2 * VB_BLOCKS, nullptr);
+            k_sum_part_to_scalar<<<1, 32, 0, stream()>>>(vb_part.p + 2 * VB_BLOCKS, dot);
+            count_launch();
+        } else k_dot<false><<<1, RED_T, 0, stream()>>>(Ok_dev(), v_dev, P, dot);
         ANGPU_CHECK_LAUNCH(); count_launch();
         dot_dev = dot;
     }
@@ -854,9 +978,9 @@ int TDVP::solve_cg(double tol, unsigned max_iter, double shift_abs, double shift
     k_dot<true><<<1, RED_T, 0, stream()>>>(r, r, n, scal + 0);
     count_launch(2);
     // convergence is decided on values summed over ranks, so that every rank takes the same decision
-    auto read_rs = [&]() -> double {
+    auto read_rs = [&](int slot) -> double {
         double* chk = d_scal.p + 12;
-        ANGPU_CUDA(cudaMemcpyAsync(chk, scal, sizeof(double), cudaMemcpyDeviceToDevice, stream()));
+        ANGPU_CUDA(cudaMemcpyAsync(chk, scal + slot, sizeof(double), cudaMemcpyDeviceToDevice, stream()));
         allreduce_sum(chk, 1);
         double hv = 0.0;
         ANGPU_CUDA(cudaMemcpyAsync(&hv, chk, sizeof(double), cudaMemcpyDeviceToHost, stream()));
@@ -864,12 +988,12 @@ int TDVP::solve_cg(double tol, unsigned max_iter, double shift_abs, double shift
         return hv;
     };
     cplx h(0.0, 0.0);
-    const double b2 = read_rs();
+    const double b2 = read_rs(0);
     if(rel_res_out) *rel_res_out = 0.0;
     unsigned it = 0;
     if(b2 > 0.0) {
         const unsigned check_every = 8;
-        const bool fused = n <= 65536;
+        const bool fused = false;      // the multi-block vector kernels (3 x ~5 us) beat the single-block fused one (~40 us at P = 16k)
         if(fused) { k_dot<false><<<1, RED_T, 0, stream()>>>(Ok_dev(), p, n, scal + 3); ANGPU_CHECK_LAUNCH(); count_launch(); }
         for(it = 1; it <= max_iter; it++) {
             if(fused) {
@@ -878,15 +1002,15 @@ int TDVP::solve_cg(double tol, unsigned max_iter, double shift_abs, double shift
                 ANGPU_CHECK_LAUNCH(); count_launch();
             } else {
                 matvec(p, Ap, nullptr, dg.p, shift_abs, shift_rel);
-                k_dot<true><<<1, RED_T, 0, stream()>>>(p, Ap, n, scal + 1);
-                k_cg_xr<<<grid_for(n), 256, 0, stream()>>>(x, r, p, Ap, scal, n);
-                k_dot<true><<<1, RED_T, 0, stream()>>>(r, r, n, scal + 2);
-                k_cg_p<<<grid_for(n), 256, 0, stream()>>>(p, r, scal, n);
-                k_cg_roll<<<1, 1, 0, stream()>>>(scal);
-                ANGPU_CHECK_LAUNCH(); count_launch(5);
+                vb_part.resize(3 * VB_BLOCKS);
+                cplx* part_pAp = vb_part.p; cplx* part_rr = vb_part.p + VB_BLOCKS;
+                k_dot_part<true><<<VB_BLOCKS, VB_T, 0, stream()>>>(p, Ap, n, part_pAp, it > 1 ? scal : nullptr);
+                k_cg_xr_mb<<<VB_BLOCKS, VB_T, 0, stream()>>>(x, r, p, Ap, scal, part_pAp, part_rr, n);
+                k_cg_p_mb<<<VB_BLOCKS, VB_T, 0, stream()>>>(p, r, scal, part_rr, n);
+                ANGPU_CHECK_LAUNCH(); count_launch(3);
             }
             if(it % check_every == 0 || it == max_iter) {
-                h.re = read_rs();
+                h.re = read_rs(fused ? 0 : 2);
                 if(rel_res_out) *rel_res_out = std::sqrt(h.re / b2);
                 if(h.re <= tol * tol * b2) break;
             }
