@@ -41,16 +41,23 @@ struct WarpScratch {
 // log psi of given configurations (psi_vector / log_psi_vector / psi_norm / ExactSummation weights;
 // source/network_functions/PsiVector.cu.template:15-133, include/ensembles/ExactSummation.hpp:54-65).
 // weight_out (optional) = exp(2 Re log psi), the un-normalised ExactSummation weight.
+// block-level scratch (after the per-warp slices): used by models that stage parameters in shared memory
+__device__ __forceinline__ unsigned char* block_scratch(unsigned pl_elems) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    return smem_raw + (size_t)(blockDim.x >> 5) * warp_slice_bytes(pl_elems);
+}
+
 template<class Psi>
 __global__ void k_log_psi(const Psi psi, const uint64_t* __restrict__ confs, size_t ns,
                           cplx* __restrict__ log_psi_out, double* __restrict__ weight_out) {
+    const unsigned char* blk = psi.stage(block_scratch(psi.payload_elems()));
     WarpScratch ws(psi.payload_elems());
     const unsigned lane = threadIdx.x & 31u, wpb = blockDim.x >> 5;
     for(size_t s = (size_t)blockIdx.x * wpb + (threadIdx.x >> 5); s < ns; s += (size_t)gridDim.x * wpb) {
         if(lane < psi.words) ws.conf[lane] = confs[s * psi.words + lane];
         __syncwarp();
-        psi.init(ws.conf, ws.pl);
-        const cplx lp = psi.log_psi(ws.conf, ws.pl);
+        psi.init(ws.conf, ws.pl, blk);
+        const cplx lp = psi.log_psi(ws.conf, ws.pl, blk);
         if(lane == 0) {
             log_psi_out[s] = lp;
             if(weight_out) weight_out[s] = exp(2.0 * lp.re);
@@ -64,12 +71,13 @@ __global__ void k_log_psi(const Psi psi, const uint64_t* __restrict__ confs, siz
 template<class Psi>
 __global__ void k_eloc(const Psi psi, const OpDev op, const uint64_t* __restrict__ confs,
                        const cplx* __restrict__ log_psi, size_t ns, cplx* __restrict__ eloc_out) {
+    const unsigned char* blk = psi.stage(block_scratch(psi.payload_elems()));
     WarpScratch ws(psi.payload_elems());
     const unsigned lane = threadIdx.x & 31u, wpb = blockDim.x >> 5;
     for(size_t s = (size_t)blockIdx.x * wpb + (threadIdx.x >> 5); s < ns; s += (size_t)gridDim.x * wpb) {
         if(lane < psi.words) ws.conf[lane] = confs[s * psi.words + lane];
         __syncwarp();
-        psi.init(ws.conf, ws.pl);
+        psi.init(ws.conf, ws.pl, blk);
         const cplx lp = log_psi[s];
         cplx diag(0.0, 0.0);
         for(unsigned n = lane; n < op.num_diag; n += 32u) diag += string_sign(op, n, ws.conf) * op.coef[n];
@@ -79,10 +87,10 @@ __global__ void k_eloc(const Psi psi, const OpDev op, const uint64_t* __restrict
             if(C.re == 0.0 && C.im == 0.0) continue;       // warp-uniform
             if(lane < psi.words) ws.conf2[lane] = ws.conf[lane] ^ op.flip[g * op.words + lane];
             __syncwarp();
-            psi.update(ws.conf, ws.conf2, ws.pl);
-            const cplx lp2 = psi.log_psi(ws.conf2, ws.pl);
+            psi.update(ws.conf, ws.conf2, ws.pl, blk);
+            const cplx lp2 = psi.log_psi(ws.conf2, ws.pl, blk);
             E += C * cexp(lp2 - lp);
-            psi.update(ws.conf2, ws.conf, ws.pl);
+            psi.update(ws.conf2, ws.conf, ws.pl, blk);
             __syncwarp();
         }
         if(lane == 0) eloc_out[s] = E;
@@ -93,13 +101,14 @@ __global__ void k_eloc(const Psi psi, const OpDev op, const uint64_t* __restrict
 // Dense log-derivative rows O[s][k] = d log psi(s) / d theta_k  (foreach_O_k of each model).
 template<class Psi>
 __global__ void k_ok(const Psi psi, const uint64_t* __restrict__ confs, size_t ns, cplx* __restrict__ O) {
+    const unsigned char* blk = psi.stage(block_scratch(psi.payload_elems()));
     WarpScratch ws(psi.payload_elems());
     const unsigned lane = threadIdx.x & 31u, wpb = blockDim.x >> 5;
     for(size_t s = (size_t)blockIdx.x * wpb + (threadIdx.x >> 5); s < ns; s += (size_t)gridDim.x * wpb) {
         if(lane < psi.words) ws.conf[lane] = confs[s * psi.words + lane];
         __syncwarp();
-        psi.init(ws.conf, ws.pl);
-        psi.O_k(ws.conf, ws.pl, O + s * (size_t)psi.P);
+        psi.init(ws.conf, ws.pl, blk);
+        psi.O_k(ws.conf, ws.pl, O + s * (size_t)psi.P, blk);
         __syncwarp();
     }
 }
@@ -110,6 +119,7 @@ __global__ void k_ok(const Psi psi, const uint64_t* __restrict__ confs, size_t n
 template<class Psi>
 __global__ void k_mc(const Psi psi, const McParams mc, uint64_t* __restrict__ conf_out,
                      cplx* __restrict__ log_psi_out, unsigned long long* __restrict__ acc_rej) {
+    const unsigned char* blk = psi.stage(block_scratch(psi.payload_elems()));
     WarpScratch ws(psi.payload_elems());
     const unsigned lane = threadIdx.x & 31u, wpb = blockDim.x >> 5;
     const unsigned chain = blockIdx.x * wpb + (threadIdx.x >> 5);
@@ -123,8 +133,8 @@ __global__ void k_mc(const Psi psi, const McParams mc, uint64_t* __restrict__ co
         ws.conf[lane] = w;
     }
     __syncwarp();
-    psi.init(ws.conf, ws.pl);
-    cplx lp = psi.log_psi(ws.conf, ws.pl);
+    psi.init(ws.conf, ws.pl, blk);
+    cplx lp = psi.log_psi(ws.conf, ws.pl, blk);
     unsigned long long t = 0, acc = 0, rej = 0;
     const unsigned therm = mc.num_therm * psi.N, per_sample = mc.num_sweeps * psi.N;
     for(unsigned s = 0; s <= mc.steps_per_chain; s++) {
@@ -134,8 +144,8 @@ __global__ void k_mc(const Psi psi, const McParams mc, uint64_t* __restrict__ co
             const unsigned site = r[0] % psi.N;
             if(lane < psi.words) ws.conf2[lane] = ws.conf[lane] ^ ((lane == (site >> 6)) ? (1ull << (site & 63u)) : 0ull);
             __syncwarp();
-            psi.update(ws.conf, ws.conf2, ws.pl);
-            const cplx nlp = psi.log_psi(ws.conf2, ws.pl);
+            psi.update(ws.conf, ws.conf2, ws.pl, blk);
+            const cplx nlp = psi.log_psi(ws.conf2, ws.pl, blk);
             const double ratio = exp(2.0 * (nlp.re - lp.re));
             const double u = u01_from_bits(r[1], r[2]);
             if(ratio > 1.0 || u <= ratio) {                 // warp-uniform (MonteCarlo.hpp:158-160)
@@ -143,7 +153,7 @@ __global__ void k_mc(const Psi psi, const McParams mc, uint64_t* __restrict__ co
                 if(lane < psi.words) ws.conf[lane] = ws.conf2[lane];
                 acc++;
             } else {
-                psi.update(ws.conf2, ws.conf, ws.pl);
+                psi.update(ws.conf2, ws.conf, ws.pl, blk);
                 rej++;
             }
             __syncwarp();

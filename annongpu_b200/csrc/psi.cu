@@ -28,17 +28,17 @@ namespace {
 
 struct WarpCfg { unsigned wpb, grid; size_t smem; };
 
-// one warp per item; warps per block limited by the per-warp scratch slice
-WarpCfg warp_cfg(unsigned pl_elems, size_t items) {
+// one warp per item; warps per block limited by the per-warp scratch slice (+ the model's block-level scratch)
+WarpCfg warp_cfg(unsigned pl_elems, size_t items, size_t block_bytes = 0) {
     const size_t slice = warp_slice_bytes(pl_elems);
-    const size_t budget = std::min<size_t>(ctx().smem_optin, 200 * 1024);
+    const size_t budget = std::min<size_t>(ctx().smem_optin, 200 * 1024) - block_bytes;
     ANGPU_REQUIRE(slice <= budget, "model scratch does not fit in shared memory");
     unsigned wpb = (unsigned)std::min<size_t>(8, budget / slice);
     // keep >= 2 blocks per SM resident when the slice allows it
     while(wpb > 1 && wpb * slice > budget / 2) wpb--;
     const size_t blocks_needed = (items + wpb - 1) / wpb;
     const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>(blocks_needed, (size_t)ctx().num_sms * 16));
-    return WarpCfg{wpb, grid, wpb * slice};
+    return WarpCfg{wpb, grid, wpb * slice + block_bytes};
 }
 
 template<class F>
@@ -49,7 +49,7 @@ void set_smem(F* kernel, size_t smem) {
 template<class Dev>
 void generic_log_psi(const Dev& d, SampleSet& S, bool es_weights) {
     if(S.ns == 0) return;
-    const WarpCfg c = warp_cfg(d.payload_elems(), S.ns);
+    const WarpCfg c = warp_cfg(d.payload_elems(), S.ns, d.block_scratch_bytes());
     set_smem(k_log_psi<Dev>, c.smem);
     k_log_psi<Dev><<<c.grid, c.wpb * 32, c.smem, stream()>>>(d, S.conf.p, S.ns, S.log_psi.p, es_weights ? S.weight.p : nullptr);
     ANGPU_CHECK_LAUNCH(); count_launch();
@@ -58,7 +58,7 @@ template<class Dev>
 void generic_eloc(const Dev& d, const Operator& op, SampleSet& S) {
     if(S.ns == 0) return;
     ANGPU_REQUIRE(op.words == d.words, "operator / wavefunction word count mismatch");
-    const WarpCfg c = warp_cfg(d.payload_elems(), S.ns);
+    const WarpCfg c = warp_cfg(d.payload_elems(), S.ns, d.block_scratch_bytes());
     set_smem(k_eloc<Dev>, c.smem);
     k_eloc<Dev><<<c.grid, c.wpb * 32, c.smem, stream()>>>(d, op.dev, S.conf.p, S.log_psi.p, S.ns, S.eloc.p);
     ANGPU_CHECK_LAUNCH(); count_launch();
@@ -66,7 +66,7 @@ void generic_eloc(const Dev& d, const Operator& op, SampleSet& S) {
 template<class Dev>
 void generic_ok(const Dev& d, SampleSet& S, size_t s0, size_t cnt, cplx* out) {
     if(cnt == 0) return;
-    const WarpCfg c = warp_cfg(d.payload_elems(), cnt);
+    const WarpCfg c = warp_cfg(d.payload_elems(), cnt, d.block_scratch_bytes());
     set_smem(k_ok<Dev>, c.smem);
     k_ok<Dev><<<c.grid, c.wpb * 32, c.smem, stream()>>>(d, S.conf.p + s0 * d.words, cnt, out);
     ANGPU_CHECK_LAUNCH(); count_launch();
@@ -75,13 +75,14 @@ template<class Dev>
 void generic_mc(const Dev& d, const McParams& mc, SampleSet& S, unsigned long long* acc_rej_dev) {
     if(mc.num_chains_local == 0) return;
     const size_t slice = warp_slice_bytes(d.payload_elems());
-    const size_t budget = std::min<size_t>(ctx().smem_optin, 200 * 1024);
+    const size_t bb = d.block_scratch_bytes();
+    const size_t budget = std::min<size_t>(ctx().smem_optin, 200 * 1024) - bb;
     ANGPU_REQUIRE(slice <= budget, "model scratch does not fit in shared memory");
     unsigned wpb = (unsigned)std::min<size_t>(4, budget / slice);
     while(wpb > 1 && wpb * slice > budget / 2) wpb--;
     const unsigned grid = ceil_div(mc.num_chains_local, wpb);
-    set_smem(k_mc<Dev>, wpb * slice);
-    k_mc<Dev><<<grid, wpb * 32, wpb * slice, stream()>>>(d, mc, S.conf.p, S.log_psi.p, acc_rej_dev);
+    set_smem(k_mc<Dev>, wpb * slice + bb);
+    k_mc<Dev><<<grid, wpb * 32, wpb * slice + bb, stream()>>>(d, mc, S.conf.p, S.log_psi.p, acc_rej_dev);
     ANGPU_CHECK_LAUNCH(); count_launch();
 }
 

@@ -28,9 +28,11 @@ struct RbmDev {
     const cplx* Wt;    // [M][N]  (for the lane-per-flip-group local-energy kernel)
 
     __host__ __device__ unsigned payload_elems() const { return M; }
+    __host__ __device__ unsigned block_scratch_bytes() const { return 0u; }
 #ifdef __CUDACC__
+    __device__ const unsigned char* stage(unsigned char*) const { return nullptr; }
     // compute_angles, PsiRBM.hpp:71-80
-    __device__ void init(const uint64_t* conf, cplx* pl) const {
+    __device__ void init(const uint64_t* conf, cplx* pl, const unsigned char* = nullptr) const {
         const unsigned lane = threadIdx.x & 31u;
         for(unsigned j = lane; j < M; j += 32u) {
             cplx a(0.0, 0.0);
@@ -40,7 +42,7 @@ struct RbmDev {
         __syncwarp();
     }
     // forward_pass + log_psi_s, PsiRBM.hpp:92-119
-    __device__ cplx log_psi(const uint64_t*, cplx* pl) const {
+    __device__ cplx log_psi(const uint64_t*, cplx* pl, const unsigned char* = nullptr) const {
         const unsigned lane = threadIdx.x & 31u;
         cplx acc(0.0, 0.0);
         for(unsigned j = lane; j < M; j += 32u) acc += act_lc(pl[j], 0u);
@@ -48,7 +50,7 @@ struct RbmDev {
         return lp + fw * acc;
     }
     // update_input_units, PsiRBM.hpp:122-157
-    __device__ void update(const uint64_t* oldc, const uint64_t* newc, cplx* pl) const {
+    __device__ void update(const uint64_t* oldc, const uint64_t* newc, cplx* pl, const unsigned char* = nullptr) const {
         const unsigned lane = threadIdx.x & 31u;
         for(unsigned w = 0; w < words; w++) {
             uint64_t diff = oldc[w] ^ newc[w];
@@ -62,7 +64,7 @@ struct RbmDev {
         __syncwarp();
     }
     // foreach_O_k, PsiRBM.hpp:161-176: O_{i*M+j} = final_weight * th0(theta_j) * s_i
-    __device__ void O_k(const uint64_t* conf, cplx* pl, cplx* row) const {
+    __device__ void O_k(const uint64_t* conf, cplx* pl, cplx* row, const unsigned char* blk = nullptr) const {
         const unsigned lane = threadIdx.x & 31u;
         for(unsigned j = lane; j < M; j += 32u) {
             const cplx t = fw * act_th(pl[j], 0u);
@@ -95,9 +97,11 @@ struct DeepDev {
 
     // scratch: angles[L1.size] | act[width] | tmp[width] | deep[num_deep]
     __host__ __device__ unsigned payload_elems() const { return L[1].size + 2u * width + num_deep; }
+    __host__ __device__ unsigned block_scratch_bytes() const { return 0u; }
 #ifdef __CUDACC__
+    __device__ const unsigned char* stage(unsigned char*) const { return nullptr; }
     // compute_angles, PsiDeep.hpp:140-157
-    __device__ void init(const uint64_t* conf, cplx* pl) const {
+    __device__ void init(const uint64_t* conf, cplx* pl, const unsigned char* = nullptr) const {
         const unsigned lane = threadIdx.x & 31u;
         const DeepLayerDev& l1 = L[1];
         for(unsigned j = lane; j < l1.size; j += 32u) {
@@ -131,9 +135,9 @@ struct DeepDev {
         for(unsigned j = lane; j < nf; j += 32u) cfma(r, act[j], final_w[j]);
         return warp_sum(r);
     }
-    __device__ cplx log_psi(const uint64_t*, cplx* pl) const { return lp + forward(pl); }
+    __device__ cplx log_psi(const uint64_t*, cplx* pl, const unsigned char* = nullptr) const { return lp + forward(pl); }
     // update_input_units / update_angles, PsiDeep.hpp:269-280, 311-343
-    __device__ void update(const uint64_t* oldc, const uint64_t* newc, cplx* pl) const {
+    __device__ void update(const uint64_t* oldc, const uint64_t* newc, cplx* pl, const unsigned char* = nullptr) const {
         const unsigned lane = threadIdx.x & 31u;
         const DeepLayerDev& l0 = L[0];
         for(unsigned w = 0; w < words; w++) {
@@ -149,7 +153,7 @@ struct DeepDev {
         }
     }
     // foreach_O_k (back-propagation), PsiDeep.hpp:347-445
-    __device__ void O_k(const uint64_t* conf, cplx* pl, cplx* row) const {
+    __device__ void O_k(const uint64_t* conf, cplx* pl, cplx* row, const unsigned char* blk = nullptr) const {
         const unsigned lane = threadIdx.x & 31u;
         cplx* angles = pl; cplx* act = pl + L[1].size; cplx* tmp = act + width; cplx* deep = tmp + width;
         for(unsigned i = lane; i < N; i += 32u) row[i] = cplx(spin_at(conf, i), 0.0);
@@ -196,6 +200,7 @@ struct DeepDev {
 // precomputed on the host, so the kernels do no div/mod.
 constexpr int CNN_MAX_LAYERS = 4;
 constexpr int CNN_MAX_LINKS = 64;
+constexpr int CNN_MAXCH = 8;          // channels per layer (the reference: max_channels_per_layer = 6)
 struct CnnLayerDev {
     unsigned nch, prev, vol, angle_off, begin_params, num_params;
     unsigned link_begin[CNN_MAX_LINKS];   // [ci * nch + cj] -> offset into params
@@ -212,29 +217,87 @@ struct CnnDev {
 
     // scratch: in[maxch*N] | out[maxch*N] | angles[num_angles]
     __host__ __device__ unsigned payload_elems() const { return 2u * maxch * N + num_angles; }
+    // the weights are staged once per block in shared memory (broadcast LDS instead of L1 round trips) when they fit
+    __host__ __device__ unsigned block_scratch_bytes() const { return (P <= 1024u) ? P * (unsigned)sizeof(cplx) : 0u; }
 #ifdef __CUDACC__
-    __device__ void init(const uint64_t*, cplx*) const {}
-    // forward_pass, PsiCNN.hpp:99-160 (angles always recorded into the warp's scratch)
-    __device__ cplx forward(const uint64_t* conf, cplx* pl) const {
+    // copies the weights into the block's shared scratch (all threads of the block call this); returns the staged copy
+    __device__ const unsigned char* stage(unsigned char* blk) const {
+        if(!block_scratch_bytes()) return nullptr;
+        // staged order per layer: [symmetry class][kernel offset c][input channel ci][output channel cj], i.e. the order
+        // in which layer_forward consumes them (one running pointer, no index arithmetic in the inner loop)
+        cplx* w = reinterpret_cast<cplx*>(blk);
+        for(unsigned l = 0; l < num_layers; l++) {
+            const CnnLayerDev& ly = L[l];
+            for(unsigned e = threadIdx.x; e < ly.num_params; e += blockDim.x) {
+                const unsigned cj = e % ly.nch, ci = (e / ly.nch) % ly.prev, c = (e / (ly.nch * ly.prev)) % ly.vol, sc = e / (ly.nch * ly.prev * ly.vol);
+                w[ly.begin_params + e] = params[ly.link_begin[ci * ly.nch + cj] + sc * ly.vol + c];
+            }
+        }
+        __syncthreads();
+        return blk;
+    }
+    __device__ void init(const uint64_t*, cplx*, const unsigned char* = nullptr) const {}
+    template<int NCH>
+    __device__ __forceinline__ void layer_forward(const CnnLayerDev& ly, unsigned l, const cplx* __restrict__ wgt, bool staged,
+                                                  const cplx* in, cplx* out, cplx* angles) const {
         const unsigned lane = threadIdx.x & 31u;
+        for(unsigned x = lane; x < N; x += 32u) {
+            const unsigned* nb = ly.nbr + x * ly.vol;
+            const unsigned wo = sym[x] * ly.vol;
+            cplx acc[NCH];
+            #pragma unroll
+            for(int cj = 0; cj < NCH; cj++) acc[cj] = cplx(0.0, 0.0);
+            if(staged) {
+                // weights of this site's symmetry class, in consumption order (see stage())
+                const cplx* wq = wgt + ly.begin_params + (size_t)wo * ly.prev * NCH;
+                for(unsigned c = 0; c < ly.vol; c++) {
+                    const cplx* src = in + nb[c];
+                    for(unsigned ci = 0; ci < ly.prev; ci++) {
+                        const cplx sv = src[ci * N];
+                        #pragma unroll
+                        for(int cj = 0; cj < NCH; cj++) cfma(acc[cj], wq[cj], sv);
+                        wq += NCH;
+                    }
+                }
+            } else {
+                for(unsigned c = 0; c < ly.vol; c++) {
+                    const unsigned src_idx = nb[c];
+                    for(unsigned ci = 0; ci < ly.prev; ci++) {
+                        const cplx sv = in[ci * N + src_idx];
+                        const unsigned* lb = ly.link_begin + ci * NCH;
+                        #pragma unroll
+                        for(int cj = 0; cj < NCH; cj++) cfma(acc[cj], wgt[lb[cj] + wo + c], sv);
+                    }
+                }
+            }
+            #pragma unroll
+            for(int cj = 0; cj < NCH; cj++) {
+                angles[ly.angle_off + (unsigned)cj * N + x] = acc[cj];
+                out[(unsigned)cj * N + x] = act_lc(acc[cj], l);
+            }
+        }
+    }
+    // forward_pass, PsiCNN.hpp:99-160 (angles always recorded into the warp's scratch).  One lane per lattice site x: the
+    // vol neighbour indices are loaded once, every input value is read once from shared memory and used for ALL output
+    // channels (register accumulators), so the inner loop is FP64-bound instead of load-bound.
+    __device__ cplx forward(const uint64_t* conf, cplx* pl, const unsigned char* blk) const {
+        const unsigned lane = threadIdx.x & 31u;
+        const cplx* __restrict__ wgt = blk ? reinterpret_cast<const cplx*>(blk) : params;
         cplx* in = pl; cplx* out = pl + maxch * N; cplx* angles = out + maxch * N;
         for(unsigned j = lane; j < N; j += 32u) in[j] = cplx(spin_at(conf, j), 0.0);
         __syncwarp();
         cplx result(0.0, 0.0);
         for(unsigned l = 0; l < num_layers; l++) {
             const CnnLayerDev& ly = L[l];
-            for(unsigned idx = lane; idx < ly.nch * N; idx += 32u) {
-                const unsigned cj = idx / N, x = idx - cj * N;
-                const unsigned* nb = ly.nbr + x * ly.vol;
-                const unsigned wo = sym[x] * ly.vol;
-                cplx acc(0.0, 0.0);
-                for(unsigned ci = 0; ci < ly.prev; ci++) {
-                    const cplx* w = params + ly.link_begin[ci * ly.nch + cj] + wo;
-                    const cplx* src = in + ci * N;
-                    for(unsigned c = 0; c < ly.vol; c++) cfma(acc, w[c], src[nb[c]]);
-                }
-                angles[ly.angle_off + idx] = acc;
-                out[idx] = act_lc(acc, l);
+            switch(ly.nch) {                 // compile-time channel count: no predicated-off FP64 work
+                case 1: layer_forward<1>(ly, l, wgt, blk != nullptr, in, out, angles); break;
+                case 2: layer_forward<2>(ly, l, wgt, blk != nullptr, in, out, angles); break;
+                case 3: layer_forward<3>(ly, l, wgt, blk != nullptr, in, out, angles); break;
+                case 4: layer_forward<4>(ly, l, wgt, blk != nullptr, in, out, angles); break;
+                case 5: layer_forward<5>(ly, l, wgt, blk != nullptr, in, out, angles); break;
+                case 6: layer_forward<6>(ly, l, wgt, blk != nullptr, in, out, angles); break;
+                case 7: layer_forward<7>(ly, l, wgt, blk != nullptr, in, out, angles); break;
+                default: layer_forward<8>(ly, l, wgt, blk != nullptr, in, out, angles); break;
             }
             __syncwarp();
             if(l + 1u < num_layers) {
@@ -246,14 +309,14 @@ struct CnnDev {
         }
         return final_factor * warp_sum(result);
     }
-    __device__ cplx log_psi(const uint64_t* conf, cplx* pl) const { return lp + forward(conf, pl); }
-    __device__ void update(const uint64_t*, const uint64_t*, cplx*) const {}   // PsiCNN.hpp:177-181
+    __device__ cplx log_psi(const uint64_t* conf, cplx* pl, const unsigned char* blk = nullptr) const { return lp + forward(conf, pl, blk); }
+    __device__ void update(const uint64_t*, const uint64_t*, cplx*, const unsigned char* = nullptr) const {}   // PsiCNN.hpp:177-181
     // foreach_O_k, PsiCNN.hpp:185-266, in gather form: each parameter is produced once (the reference emits
     // a k several times and its consumers accumulate atomically, Appendix A.9).
-    __device__ void O_k(const uint64_t* conf, cplx* pl, cplx* row) const {
+    __device__ void O_k(const uint64_t* conf, cplx* pl, cplx* row, const unsigned char* blk = nullptr) const {
         const unsigned lane = threadIdx.x & 31u;
         cplx* delta = pl; cplx* back = pl + maxch * N; cplx* angles = back + maxch * N;
-        (void)forward(conf, pl);
+        (void)forward(conf, pl, blk);
         __syncwarp();
         const unsigned lastc = L[num_layers - 1u].nch;
         for(unsigned idx = lane; idx < lastc * N; idx += 32u) back[idx] = cplx(final_factor, 0.0);
@@ -314,9 +377,11 @@ struct ClassicalDev {
     CnnDev   ref;
 
     __host__ __device__ unsigned payload_elems() const { return (order > 1u && has_ref) ? ref.payload_elems() : 1u; }
+    __host__ __device__ unsigned block_scratch_bytes() const { return 0u; }
 #ifdef __CUDACC__
-    __device__ void init(const uint64_t*, cplx*) const {}
-    __device__ cplx log_psi(const uint64_t* conf, cplx* pl) const {
+    __device__ const unsigned char* stage(unsigned char*) const { return nullptr; }
+    __device__ void init(const uint64_t*, cplx*, const unsigned char* = nullptr) const {}
+    __device__ cplx log_psi(const uint64_t* conf, cplx* pl, const unsigned char* = nullptr) const {
         const unsigned lane = threadIdx.x & 31u;
         cplx acc(0.0, 0.0);
         for(unsigned n = lane; n < num_ops; n += 32u) acc += params[n] * fast_local_energy_serial(ops[n], conf);
@@ -324,8 +389,8 @@ struct ClassicalDev {
         if(order > 1u && has_ref) r += ref.log_psi(conf, pl);
         return r;
     }
-    __device__ void update(const uint64_t*, const uint64_t*, cplx*) const {}
-    __device__ void O_k(const uint64_t* conf, cplx* pl, cplx* row) const {
+    __device__ void update(const uint64_t*, const uint64_t*, cplx*, const unsigned char* = nullptr) const {}
+    __device__ void O_k(const uint64_t* conf, cplx* pl, cplx* row, const unsigned char* blk = nullptr) const {
         const unsigned lane = threadIdx.x & 31u;
         for(unsigned n = lane; n < num_ops; n += 32u) row[n] = fast_local_energy_serial(ops[n], conf);
         if(order > 1u && has_ref) ref.O_k(conf, pl, row + num_ops);
