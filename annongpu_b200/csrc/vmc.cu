@@ -188,6 +188,28 @@ __global__ void __launch_bounds__(256) k_rowdot_dense(const cplx* __restrict__ O
     if(threadIdx.x == 0) { cplx r(0.0, 0.0); for(int i = 0; i < 8; i++) r += sm[i]; a[s] = r; }
 }
 
+// out = (S + shift) v with the dense, already centred and rank-reduced S (row-major, P x P): one block per row, 16-byte
+// coalesced loads; S is streamed once per product (P^2 x 16 B), v stays in L2.  HBM-bound.
+__global__ void __launch_bounds__(256) k_smat_vec(const cplx* __restrict__ Sm, const cplx* __restrict__ v, const double* __restrict__ diag,
+                                                  double shift_abs, double shift_rel, unsigned P, cplx* __restrict__ out) {
+    const size_t i = blockIdx.x;
+    const cplx* row = Sm + i * P;
+    cplx a0(0.0, 0.0), a1(0.0, 0.0);
+    unsigned k = threadIdx.x;
+    for(; k + 256u < P; k += 512u) { cfma(a0, ldg(row + k), v[k]); cfma(a1, ldg(row + k + 256u), v[k + 256u]); }
+    if(k < P) cfma(a0, ldg(row + k), v[k]);
+    __shared__ cplx sm[8];
+    cplx acc = warp_sum(a0 + a1);
+    if((threadIdx.x & 31u) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if(threadIdx.x == 0) {
+        cplx r(0.0, 0.0);
+        for(int w = 0; w < 8; w++) r += sm[w];
+        if(diag) r += (shift_abs + shift_rel * diag[i]) * v[i];
+        out[i] = r;
+    }
+}
+
 // a_s = sum_j T_sj (sum_i sigma_si v_ij)   (PsiRBM factorised rows).  Block = 32 samples x all j; thread = 8 samples x 2
 // columns (j, j+64) per 128-column block; signs staged in shared memory as +-1.0 doubles [site][sample] so that the 8
 // samples of a thread are 4 broadcast LDS.128; v is read once per block (L1/L2): ns/32 re-reads instead of ns/8.
@@ -897,8 +919,13 @@ void TDVP::build_S() {
 }
 
 // out = S v (+ (shift_abs + shift_rel diag) v when diag != null).  dot_dev: device scalar Obar . v if already known.
-void TDVP::matvec(const cplx* v_dev, cplx* out_dev, const cplx* dot_dev, const double* diag, double shift_abs, double shift_rel) {
+void TDVP::matvec(const cplx* v_dev, cplx* out_dev, const cplx* dot_dev, const double* diag, double shift_abs, double shift_rel, bool allow_S) {
     ANGPU_REQUIRE(evaluated, "TDVP: call eval / eval_F first");
+    if(allow_S && have_S && !factorised) {      // S already built (eval): one pass over P^2 instead of two over Ns x P
+        k_smat_vec<<<P, 256, 0, stream()>>>(Smat.p, v_dev, diag, shift_abs, shift_rel, P, out_dev);
+        ANGPU_CHECK_LAUNCH(); count_launch();
+        return;
+    }
     const size_t ns = S.ns;
     row_a.resize(std::max<size_t>(1, ns));
     if(ns) {
@@ -963,6 +990,10 @@ static void tdvp_diag(TDVP& t, DevBuf<double>& dbuf) {
 
 int TDVP::solve_cg(double tol, unsigned max_iter, double shift_abs, double shift_rel, cplx rhs_phase, cplx* x_host, double* rel_res_out) {
     ANGPU_REQUIRE(evaluated, "TDVP: call eval / eval_F first");
+    // with a dense S at hand (eval) the products stream S; ANGPU_CG_MATRIX_FREE=1 forces the O-based products
+    const char* env_free = getenv("ANGPU_CG_MATRIX_FREE");
+    const bool force_free = env_free && env_free[0] == '1';
+    const bool use_S = have_S && !factorised && !force_free;
     mark(5);
     const size_t n = P;
     DevBuf<double> dg;
@@ -1001,7 +1032,7 @@ int TDVP::solve_cg(double tol, unsigned max_iter, double shift_abs, double shift
                 k_cg_fused<<<1, RED_T, 0, stream()>>>(x, r, p, Ap, Ok_dev(), scal, n);
                 ANGPU_CHECK_LAUNCH(); count_launch();
             } else {
-                matvec(p, Ap, nullptr, dg.p, shift_abs, shift_rel);
+                matvec(p, Ap, nullptr, dg.p, shift_abs, shift_rel, use_S);
                 vb_part.resize(3 * VB_BLOCKS);
                 cplx* part_pAp = vb_part.p; cplx* part_rr = vb_part.p + VB_BLOCKS;
                 k_dot_part<true><<<VB_BLOCKS, VB_T, 0, stream()>>>(p, Ap, n, part_pAp, it > 1 ? scal : nullptr);

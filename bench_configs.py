@@ -83,6 +83,19 @@ def main():
         ph = t.phase_ms
         x = t.solve(shift_abs=0.0, shift_rel=1e-3)
         ms_solve = t.phase_ms["solve"]
+        import numpy as np
+        return_cg = {}
+        for label, env in (("cg_on_dense_S", "0"), ("cg_matrix_free_on_O", "1")):
+            os.environ["ANGPU_CG_MATRIX_FREE"] = env
+            x_cg, it_cg, rr_cg = t.solve_cg(tol=1e-6, max_iter=3000, shift_abs=0.0, shift_rel=1e-3)
+            ms_cg = t.phase_ms["solve"]
+            bytes_per_it = (P * P * 16.0) if env == "0" else (2.0 * ns * P * 16)
+            return_cg[label] = {"iterations": it_cg, "rel_residual": rr_cg, "ms": ms_cg, "ms_per_iteration": ms_cg / max(1, it_cg),
+                                "algorithmic_GB_per_s": bytes_per_it * it_cg / (ms_cg * 1e-3) / 1e9,
+                                "bytes_per_iteration": bytes_per_it,
+                                "max |x_cg - x_dense| / max |x_dense|": float(np.abs(x_cg - x).max() / np.abs(x).max())}
+        os.environ["ANGPU_CG_MATRIX_FREE"] = "0"
+        cg = return_cg
         flops_S = 4.0 * ns * P * P
         # opt-in tensor-core rebuild of S from the same samples (3xTF32 on tcgen05): time and deviation from the fp64 S
         import numpy as np
@@ -103,7 +116,7 @@ def main():
                           "phase_ms": ph, "ms_dense_solve": ms_solve,
                           "S_build": {"ms": ph["s_build"], "TFLOP/s (4 Ns P^2)": flops_S / (ph["s_build"] * 1e-3) / 1e12,
                                       "fp64_peak_measured": fp64_peak, "frac_of_fp64_peak": flops_S / (ph["s_build"] * 1e-3) / 1e12 / fp64_peak},
-                          "S_build_tensorcore": tc,
+                          "S_build_tensorcore": tc, "cg": cg,
                           "acceptance": mc.acceptance_rate, "E": t.E_local.real, "x_norm": float(abs(x).max())}))
 
     if "C5" in todo:

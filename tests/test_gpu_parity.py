@@ -352,3 +352,28 @@ def test_tensorcore_S_build_matches_fp64(gpu, name, ns_mc):
         S64 = t.S_matrix
         t.build_S_tensorcore()
         assert np.abs(t.S_matrix - S64).max() <= 1e-5 * np.abs(S64).max()
+
+
+def test_cg_on_dense_S_matches_matrix_free_and_cholesky(gpu):
+    """After eval() the CG products stream the dense S (k_smat_vec); ANGPU_CG_MATRIX_FREE=1 forces the O-based
+    products.  Both, and the Cholesky solve, must give the same solution of (S + shift) x = F."""
+    import os
+    spec, H, N = zoo()["deep2"]
+    psi, op = make_psi(gpu, spec), make_op(gpu, H)
+    ens = gpu.MonteCarloSpins(4096, 1, 5, 4096, True, seed=5)
+    t = gpu.TDVP(psi.num_params, True)
+    t.eval(op, psi, ens)
+    S, F = t.S_matrix, t.F_vector
+    A = S + 1e-3 * np.diag(np.diag(S).real) + 1e-4 * np.eye(psi.num_params)
+    x_d = t.solve(shift_abs=1e-4, shift_rel=1e-3)
+    assert np.linalg.norm(A @ x_d - F) <= 1e-8 * np.linalg.norm(F)
+    try:
+        xs = {}
+        for env in ("0", "1"):
+            os.environ["ANGPU_CG_MATRIX_FREE"] = env
+            x, it, rr = t.solve_cg(tol=1e-10, max_iter=20000, shift_abs=1e-4, shift_rel=1e-3)
+            assert np.linalg.norm(A @ x - F) <= 1e-7 * np.linalg.norm(F), (env, it, rr)
+            xs[env] = x
+    finally:
+        os.environ["ANGPU_CG_MATRIX_FREE"] = "0"
+    assert rel_err(xs["0"], xs["1"]) <= 1e-5
