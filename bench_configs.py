@@ -81,19 +81,28 @@ def main():
         t.set_profile(True)
         ms_eval = timed(lambda: t.eval(op, psi, mc), args.steps, warmup=1)
         ph = t.phase_ms
-        x = t.solve(shift_abs=0.0, shift_rel=1e-3)
-        ms_solve = t.phase_ms["solve"]
         import numpy as np
+        solve_ms = []
+        for _ in range(3):                        # the first call creates the cuSOLVER handle and workspace
+            x = t.solve(shift_abs=0.0, shift_rel=1e-3)
+            solve_ms.append(t.phase_ms["solve"])
+        ms_solve = min(solve_ms)
+        Sm, Fv = t.S_matrix, t.F_vector
+        Sm[np.diag_indices(P)] *= 1.0 + 1e-3
+        solve_residual = float(np.linalg.norm(Sm @ x - Fv) / np.linalg.norm(Fv))
+        del Sm
         return_cg = {}
         for label, env in (("cg_on_dense_S", "0"), ("cg_matrix_free_on_O", "1")):
             os.environ["ANGPU_CG_MATRIX_FREE"] = env
-            x_cg, it_cg, rr_cg = t.solve_cg(tol=1e-6, max_iter=3000, shift_abs=0.0, shift_rel=1e-3)
+            # a bandwidth probe of the two S.v products, NOT a solve: at this shift cond(S) is far too large for CG
+            # (the Cholesky solve above is the C4 path), so the iteration count is capped
+            x_cg, it_cg, rr_cg = t.solve_cg(tol=1e-6, max_iter=300, shift_abs=0.0, shift_rel=1e-3)
             ms_cg = t.phase_ms["solve"]
             bytes_per_it = (P * P * 16.0) if env == "0" else (2.0 * ns * P * 16)
             return_cg[label] = {"iterations": it_cg, "rel_residual": rr_cg, "ms": ms_cg, "ms_per_iteration": ms_cg / max(1, it_cg),
                                 "algorithmic_GB_per_s": bytes_per_it * it_cg / (ms_cg * 1e-3) / 1e9,
                                 "bytes_per_iteration": bytes_per_it,
-                                "max |x_cg - x_dense| / max |x_dense|": float(np.abs(x_cg - x).max() / np.abs(x).max())}
+                                "note": "capped at 300 iterations: mat-vec bandwidth probe, not converged"}
         os.environ["ANGPU_CG_MATRIX_FREE"] = "0"
         cg = return_cg
         flops_S = 4.0 * ns * P * P
@@ -113,7 +122,7 @@ def main():
               "includes": "fp64 centring + TF32 hi/lo packing (k_pack_planes) + k_sbuild_tf32"}
         print(json.dumps({"config": "C4", "what": "PsiDeep 64->64->64 (P=8384), 8x8 TFIM (192 strings), TDVP.eval: sampling + E_loc + O_k + dense S, "
                           "then Cholesky solve", "samples": ns, "ms_eval": ms_eval, "sr_steps_per_s": 1e3 / (ms_eval + ms_solve),
-                          "phase_ms": ph, "ms_dense_solve": ms_solve,
+                          "phase_ms": ph, "ms_dense_solve": ms_solve, "ms_dense_solve_calls": solve_ms, "dense_solve_rel_residual": solve_residual,
                           "S_build": {"ms": ph["s_build"], "TFLOP/s (4 Ns P^2)": flops_S / (ph["s_build"] * 1e-3) / 1e12,
                                       "fp64_peak_measured": fp64_peak, "frac_of_fp64_peak": flops_S / (ph["s_build"] * 1e-3) / 1e12 / fp64_peak},
                           "S_build_tensorcore": tc, "cg": cg,

@@ -78,8 +78,16 @@ def lib():
         L.ref_tdvp_get.argtypes = [vp, vp, vp, vp, vp]
         L.ref_tdvp_get_samples.argtypes = [vp, vp, vp]
         L.ref_tdvp_S_dot_vector.argtypes = [vp, vp, i32, vp, vp]
+        L.ref_set_gpu.argtypes = [i32]
+        L.ref_device_synchronize.restype = i32
         _lib = L
     return _lib
+
+
+def set_gpu(on):
+    """Objects created afterwards use the reference's own CUDA path (gpu=true).  Timing baseline only
+    (tools/ref_gpu_bench.py); the parity oracle is the default gpu=false host path."""
+    lib().ref_set_gpu(1 if on else 0)
 
 
 def _c128(x):

@@ -1,9 +1,12 @@
 // TEST INFRASTRUCTURE — NOT PRODUCT CODE.
 //
 // C interface over the UNMODIFIED reference (heikoburau/ANNonGPU) compiled from the sources
-// where they lie under /root/reference (see oracle/Makefile).  Only the reference's serial host
-// path (gpu=false) is exercised: that path makes no CUDA calls and is the bit-for-bit CPU
-// restatement of the reference's own arithmetic (include/cuda_kernel_defines.h:16-29).
+// where they lie under /root/reference (see oracle/Makefile).  By default only the reference's
+// serial host path (gpu=false) is exercised: that path makes no CUDA calls and is the bit-for-bit
+// CPU restatement of the reference's own arithmetic (include/cuda_kernel_defines.h:16-29).
+// ref_set_gpu(1) switches every object created afterwards to the reference's own CUDA path
+// (gpu=true): used ONLY by tools/ref_gpu_bench.py to time the reference's kernels on the same B200
+// as a second baseline.
 //
 // This file contains no reference source: it only *calls* the reference's public C++ API
 //   PsiRBM / PsiDeep / PsiCNN / PsiClassicalFP / PsiClassicalANN   (include/quantum_state/*.hpp)
@@ -40,6 +43,8 @@
 using namespace ann_on_gpu;
 using cplx = std::complex<double>;
 
+static bool g_gpu = false;    // see ref_set_gpu
+
 struct RawExpr {
     unsigned int     n;
     const double*    coeffs;   // interleaved
@@ -60,6 +65,8 @@ StandartOperator<PauliString>::StandartOperator(const RawExpr& expr, const bool 
         this->coefficients[i] = complex_t(expr.coeffs[2 * i], expr.coeffs[2 * i + 1]);
         this->quantum_strings[i] = PauliString(expr.a[i], expr.b[i]);
     }
+    this->coefficients.update_device();       // no-ops for gpu == false
+    this->quantum_strings.update_device();
     this->kernel().num_strings = expr.n;
     this->kernel().coefficients = this->coefficients.data();
     this->kernel().quantum_strings = this->quantum_strings.data();
@@ -137,7 +144,7 @@ void ref_activation(double re, double im, unsigned int layer, double* lc_out, do
 
 void* ref_op_create(unsigned int n, const double* coeffs, const uint64_t* a, const uint64_t* b) {
     RawExpr e{n, coeffs, a, b};
-    return new Operator(e, false);
+    return new Operator(e, g_gpu);
 }
 void ref_op_destroy(void* op) { delete static_cast<Operator*>(op); }
 
@@ -145,7 +152,7 @@ void ref_op_destroy(void* op) { delete static_cast<Operator*>(op); }
 
 void* ref_rbm_create(unsigned int N, unsigned int M, const double* W,
                      double fw_re, double fw_im, double lp_re, double lp_im) {
-    return new PsiRBM(ctensor2(W, N, M), cplx(fw_re, fw_im), cplx(lp_re, lp_im), false);
+    return new PsiRBM(ctensor2(W, N, M), cplx(fw_re, fw_im), cplx(lp_re, lp_im), g_gpu);
 }
 
 // hidden layer l (0-based): sizes[l] units, conn[l] lhs-connections per unit;
@@ -167,7 +174,7 @@ void* ref_deep_create(unsigned int num_sites, unsigned int N, const double* inpu
     }
     return new PsiDeep(
         num_sites, ctensor1(input_weights, N), b_list, c_list, w_list,
-        ctensor1(final_weights, sizes[num_hidden - 1]), cplx(lp_re, lp_im), false
+        ctensor1(final_weights, sizes[num_hidden - 1]), cplx(lp_re, lp_im), g_gpu
     );
 }
 
@@ -183,7 +190,7 @@ void* ref_cnn_create(const unsigned int* extent, unsigned int num_layers, const 
         xt::pytensor<unsigned int, 2>(connectivity, {(long)num_layers, 3l}),
         xt::pytensor<unsigned int, 1>(symmetry_classes, {N}),
         ctensor1(params, num_params),
-        final_factor, cplx(lp_re, lp_im), false
+        final_factor, cplx(lp_re, lp_im), g_gpu
     );
 }
 void ref_cnn_init_gradient(void* psi, unsigned int num_steps) {
@@ -200,12 +207,12 @@ void* ref_classical_create(unsigned int num_sites, unsigned int order, unsigned 
     const cplx lp(lp_re, lp_im);
     if(cnn_ref == nullptr) {
         PsiFullyPolarized fp(num_sites, lp);
-        if(order == 1u) return new PsiClassicalFP<1u>(num_sites, H_local, p, fp, lp, false);
-        return new PsiClassicalFP<2u>(num_sites, H_local, p, fp, lp, false);
+        if(order == 1u) return new PsiClassicalFP<1u>(num_sites, H_local, p, fp, lp, g_gpu);
+        return new PsiClassicalFP<2u>(num_sites, H_local, p, fp, lp, g_gpu);
     }
     auto& ref = *static_cast<PsiCNN*>(cnn_ref);
-    if(order == 1u) return new PsiClassicalANN<1u>(num_sites, H_local, p, ref, lp, false);
-    return new PsiClassicalANN<2u>(num_sites, H_local, p, ref, lp, false);
+    if(order == 1u) return new PsiClassicalANN<1u>(num_sites, H_local, p, ref, lp, g_gpu);
+    return new PsiClassicalANN<2u>(num_sites, H_local, p, ref, lp, g_gpu);
 }
 
 void ref_psi_destroy(int kind, void* h) { with_psi(kind, h, [](auto& psi) { delete &psi; }); }
@@ -234,9 +241,11 @@ void ref_psi_set_log_prefactor(int kind, void* h, double re, double im) {
 
 // ---------------------------------------------------------------- ensembles
 
-void* ref_es_create(unsigned int num_sites) { return new ExactSummationSpins(num_sites, false); }
+void ref_set_gpu(int on) { g_gpu = on != 0; }
+int  ref_device_synchronize() { return (int)cudaDeviceSynchronize(); }
+void* ref_es_create(unsigned int num_sites) { return new ExactSummationSpins(num_sites, g_gpu); }
 void* ref_mc_create(unsigned int num_samples, unsigned int num_sweeps, unsigned int num_therm, unsigned int num_chains) {
-    return new MonteCarloSpins(num_samples, num_sweeps, num_therm, num_chains, Update_Policy<Spins>(), false);
+    return new MonteCarloSpins(num_samples, num_sweeps, num_therm, num_chains, Update_Policy<Spins>(), g_gpu);
 }
 void ref_ens_destroy(int kind, void* h) { with_ens(kind, h, [](auto& e) { delete &e; }); }
 unsigned int ref_ens_num_steps(int kind, void* h) {
@@ -287,14 +296,14 @@ void ref_apply_operator(int kind, void* h, void* op, int ek, void* e, double* ou
 // ---------------------------------------------------------------- ExpectationValue
 
 void ref_expectation(int kind, void* h, void* op, int ek, void* e, double* out) {
-    ExpectationValue ev(false);
+    ExpectationValue ev(g_gpu);
     with_psi(kind, h, [&](auto& psi) {
         with_ens(ek, e, [&](auto& ens) { store(out, ev(*static_cast<Operator*>(op), psi, ens)); });
     });
 }
 // out = {fluctuation, Re <A>, Im <A>}
 void ref_fluctuation(int kind, void* h, void* op, int ek, void* e, double* out) {
-    ExpectationValue ev(false);
+    ExpectationValue ev(g_gpu);
     with_psi(kind, h, [&](auto& psi) {
         with_ens(ek, e, [&](auto& ens) {
             const auto r = ev.fluctuation(*static_cast<Operator*>(op), psi, ens);
@@ -303,7 +312,7 @@ void ref_fluctuation(int kind, void* h, void* op, int ek, void* e, double* out) 
     });
 }
 void ref_gradient(int kind, void* h, void* op, int ek, void* e, double* grad_out, double* E_out) {
-    ExpectationValue ev(false);
+    ExpectationValue ev(g_gpu);
     with_psi(kind, h, [&](auto& psi) {
         with_ens(ek, e, [&](auto& ens) {
             const auto r = ev.gradient(*static_cast<Operator*>(op), psi, ens);
@@ -314,7 +323,7 @@ void ref_gradient(int kind, void* h, void* op, int ek, void* e, double* grad_out
 
 // ---------------------------------------------------------------- TDVP
 
-void* ref_tdvp_create(unsigned int num_params) { return new TDVP(num_params, false); }
+void* ref_tdvp_create(unsigned int num_params) { return new TDVP(num_params, g_gpu); }
 void  ref_tdvp_destroy(void* t) { delete static_cast<TDVP*>(t); }
 
 void ref_tdvp_eval(void* t, int kind, void* h, void* op, int ek, void* e) {
