@@ -1,8 +1,10 @@
 // Host-side wavefunction objects: parameter bookkeeping + kernel launches.
 #include "psi.hpp"
 #include "rbm_kernels.cuh"
+#include "deep_kernels.cuh"
 #include <algorithm>
 #include <set>
+#include <string>
 
 namespace angpu {
 
@@ -300,6 +302,26 @@ void PsiDeep::upload() {
         L.d_lhs_w.upload(L.lhs_w); L.d_rhs_w.upload(L.rhs_w); L.d_bias.upload(L.bias);
     }
     d_final.upload(final_weights);
+    // eligibility of the block-per-chain sampler + its dense tables: layer l as wd[k][j] = weight of input k for unit j
+    // (0 where unconnected), [N][64] for the first layer followed by [64][64] per deep layer
+    block_sampler_ok = (num_layers == 3u || num_layers == 4u);
+    for(unsigned l = 1; l < num_layers; l++) if(layers[l].size > (unsigned)DEEP_BLK_W) block_sampler_ok = false;
+    if(block_sampler_ok) {
+        std::vector<cplx> t((size_t)(N + (num_layers - 2u) * DEEP_BLK_W) * DEEP_BLK_W, cplx(0.0, 0.0));
+        std::vector<unsigned char> seen(t.size(), 0);
+        size_t base = 0;
+        for(unsigned l = 1; l < num_layers && block_sampler_ok; l++) {
+            const Layer& L = layers[l];
+            for(unsigned i = 0; i < L.conn && block_sampler_ok; i++)
+                for(unsigned j = 0; j < L.size; j++) {
+                    const size_t at = base + (size_t)L.lhs_c[(size_t)i * L.size + j] * DEEP_BLK_W + j;
+                    if(seen[at]) { block_sampler_ok = false; break; }      // a unit reading the same input twice
+                    seen[at] = 1; t[at] = L.lhs_w[(size_t)i * L.size + j];
+                }
+            base += (size_t)(l == 1 ? N : (unsigned)DEEP_BLK_W) * DEEP_BLK_W;
+        }
+        if(block_sampler_ok) d_w1dense.upload(t);
+    }
 }
 DeepDev PsiDeep::dev() const {
     DeepDev d{};
@@ -336,7 +358,16 @@ void PsiDeep::set_params(const cplx* in) {
 void PsiDeep::log_psi(SampleSet& S, bool es_weights) { generic_log_psi(dev(), S, es_weights); }
 void PsiDeep::eloc(const Operator& op, SampleSet& S) { generic_eloc(dev(), op, S); }
 void PsiDeep::ok_rows(SampleSet& S, size_t s0, size_t cnt, cplx* out) { generic_ok(dev(), S, s0, cnt, out); }
-void PsiDeep::mc_sample(const McParams& mc, SampleSet& S, unsigned long long* a) { generic_mc(dev(), mc, S, a); }
+void PsiDeep::mc_sample(const McParams& mc, SampleSet& S, unsigned long long* a) {
+    const char* env_s = getenv("ANGPU_DEEP_SAMPLER");          // "generic" forces the warp-per-chain kernel (tests, A/B timing)
+    const bool force_generic = env_s && std::string(env_s) == "generic";
+    if(!block_sampler_ok || force_generic) { generic_mc(dev(), mc, S, a); return; }
+    if(mc.num_chains_local == 0) return;
+    const unsigned grid = ceil_div(mc.num_chains_local, (unsigned)DEEP_BLK_NC);
+    if(num_layers == 3u) k_mc_deep_block<1><<<grid, DEEP_BLK_T, 0, stream()>>>(dev(), d_w1dense.p, mc, S.conf.p, S.log_psi.p, a);
+    else                 k_mc_deep_block<2><<<grid, DEEP_BLK_T, 0, stream()>>>(dev(), d_w1dense.p, mc, S.conf.p, S.log_psi.p, a);
+    ANGPU_CHECK_LAUNCH(); count_launch();
+}
 
 // ---------------------------------------------------------------------------------------- PsiCNN
 

@@ -83,6 +83,10 @@ struct PsiDeep : Psi {
     std::vector<Layer> layers;          // [0] = input layer
     std::vector<cplx> input_weights, final_weights;
     DevBuf<cplx> d_final;
+    // block-per-chain sampler (deep_kernels.cuh): eligible with 2 or 3 hidden layers, each <= 64 wide, no unit reading
+    // the same input twice; d_w1dense = the layers as dense tables (first layer [N][64], then [64][64] per deep layer)
+    bool block_sampler_ok = false;
+    DevBuf<cplx> d_w1dense;
 
     PsiDeep(unsigned num_sites_, unsigned N_, const cplx* input_weights_, unsigned num_hidden, const unsigned* sizes,
             const unsigned* conn, const cplx* biases, const unsigned* lhs_connections, const cplx* lhs_weights,

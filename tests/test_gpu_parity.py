@@ -176,7 +176,7 @@ def test_expectation_list_and_hermitian_identity(gpu, port):
 
 # ------------------------------------------------------------------------------------------------ Monte Carlo
 
-@pytest.mark.parametrize("name", ["rbm10", "rbm8_cfw", "rbm12_m40", "rbm_wide", "deep2", "cnn"])
+@pytest.mark.parametrize("name", ["rbm10", "rbm8_cfw", "rbm12_m40", "rbm_wide", "deep1", "deep2", "deep3", "cnn"])
 def test_mc_chains_identical_to_oracle(gpu, port, name):
     """Same Philox stream, same proposals: the sampled configurations must coincide chain by chain."""
     spec, H, N = {**zoo(), **wide_zoo()}[name]
@@ -377,3 +377,22 @@ def test_cg_on_dense_S_matches_matrix_free_and_cholesky(gpu):
     finally:
         os.environ["ANGPU_CG_MATRIX_FREE"] = "0"
     assert rel_err(xs["0"], xs["1"]) <= 1e-5
+
+
+def test_deep_block_sampler_matches_generic_at_c4_shape(gpu):
+    """PsiDeep 64-64-64 (C4): the block-per-chain sampler (deep_kernels.cuh) and the generic warp-per-chain kernel run the
+    same Philox stream; configurations must coincide and log psi agree to rounding."""
+    import os
+    spec, H = F.config_C4()
+    psi = make_psi(gpu, spec)
+    out = {}
+    try:
+        for mode in ("block", "generic"):
+            os.environ["ANGPU_DEEP_SAMPLER"] = mode
+            mc = gpu.MonteCarloSpins(98 * 2, 1, 4, 98, True, seed=21)      # 98: a ragged last block of the 4-chain kernel
+            out[mode] = mc.sample(psi) + (mc.acceptances,)
+    finally:
+        os.environ["ANGPU_DEEP_SAMPLER"] = "block"
+    assert np.array_equal(out["block"][0], out["generic"][0])
+    assert rel_err(out["block"][1], out["generic"][1]) <= 1e-10
+    assert out["block"][2] == out["generic"][2]
