@@ -73,12 +73,15 @@ _SIGNATURES = {
     "angpu_expval_destroy": [vp],
     "angpu_expectation": [vp, vp, vp, vp, vp],
     "angpu_expectation_many": [vp, u32, vp, vp, vp, vp],
+    "angpu_expectation_reweighted": [vp, vp, vp, vp, vp, vp],
+    "angpu_exp_sigma_z": [vp, vp, vp, vp, vp],
     "angpu_fluctuation": [vp, vp, vp, vp, vp, vp],
     "angpu_gradient": [vp, vp, vp, vp, vp, vp],
     "angpu_tdvp_create": [u32, vp],
     "angpu_tdvp_destroy": [vp],
     "angpu_tdvp_eval": [vp, vp, vp, vp],
     "angpu_tdvp_eval_F": [vp, vp, vp, vp],
+    "angpu_tdvp_eval_reweighted": [vp, vp, vp, vp, vp],
     "angpu_tdvp_get_S": [vp, vp],
     "angpu_tdvp_get_F": [vp, vp],
     "angpu_tdvp_get_O_k": [vp, vp],

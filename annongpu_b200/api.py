@@ -418,10 +418,27 @@ class PsiCNN(_Psi):
 
 
 class PsiFullyPolarized:
-    """PsiFullyPolarized(num_sites, log_prefactor) (pyANNonGPU/main.cpp.template:284-291): log psi = 0."""
+    """PsiFullyPolarized(num_sites, log_prefactor) (pyANNonGPU/main.cpp.template:284-291): log psi(s) = 0 for every s,
+    no parameters (include/quantum_state/PsiFullyPolarized.hpp:41-49 ignores log_prefactor).  As a sampling
+    distribution (TDVP.eval_with_psi_ref of a PsiClassicalFP) it is the uniform one; on the device it is a PsiClassical
+    with no local operators."""
 
     def __init__(self, num_sites, log_prefactor=0.0):
-        self.num_sites, self.log_prefactor, self.num_params, self.gpu = int(num_sites), complex(log_prefactor), 0, False
+        self.num_sites = self.N = int(num_sites)
+        self.log_prefactor, self.num_params, self.gpu = complex(log_prefactor), 0, True
+        self._handle = None
+
+    @property
+    def _h(self):
+        if self._handle is None:
+            self._handle = C.c_void_p()
+            call("angpu_classical_create", self.num_sites, 1, 0, None, None, 0, None, _p(_pair(0.0)), C.byref(self._handle))
+        return self._handle
+
+    def __del__(self):
+        if getattr(self, "_handle", None):
+            lib.angpu_psi_destroy(self._handle)
+            self._handle = None
 
 
 class _PsiClassical(_Psi):
@@ -562,7 +579,15 @@ class ExpectationValue:
             lib.angpu_expval_destroy(self._h)
             self._h = None
 
-    def __call__(self, operator, psi, ensemble):
+    def __call__(self, operator, psi, *args):
+        """(operator | [operators], psi, ensemble) or the importance-reweighted (operator, psi, psi_sampling, ensemble)."""
+        if len(args) == 2:
+            psi_sampling, ensemble = args
+            op = _match(operator, psi)
+            out = np.empty(2)
+            call("angpu_expectation_reweighted", self._h, op._h, psi._h, psi_sampling._h, ensemble._h, _p(out))
+            return complex(out[0], out[1])
+        (ensemble,) = args
         if isinstance(operator, (list, tuple)):
             ops = [_match(o, psi) for o in operator]
             handles = (C.c_void_p * max(1, len(ops)))(*[o._h for o in ops])
@@ -585,6 +610,17 @@ class ExpectationValue:
         g, m = np.empty(psi.num_params, dtype=np.complex128), np.empty(2)
         call("angpu_gradient", self._h, op._h, psi._h, ensemble._h, _p(g), _p(m))
         return g, complex(m[0], m[1])
+
+    def exp_sigma_z(self, operator, psi, ensemble):
+        """sum_s w_s exp(sum_n c_n coefficient_n(s)) (ExpectationValue.cu.template:52-82)."""
+        op = _match(operator, psi)
+        out = np.empty(2)
+        call("angpu_exp_sigma_z", self._h, op._h, psi._h, ensemble._h, _p(out))
+        return complex(out[0], out[1])
+
+    def gradient_with_noise(self, operator, psi, ensemble):
+        raise NotImplementedError("gradient_with_noise: the reference's body is commented out and returns uninitialised "
+                                  "arrays (ExpectationValue.cu.template:276-333); there is nothing to reproduce")
 
 
 class TDVP:
@@ -612,6 +648,16 @@ class TDVP:
         op = _match(operator, psi)
         self._keep = (op, psi, ensemble)
         call("angpu_tdvp_eval_F", self._h, op._h, psi._h, ensemble._h)
+
+    def eval_with_psi_ref(self, operator, psi, ensemble, psi_sampling=None):
+        """TDVP::eval(..., true_t) (include/network_functions/TDVP.hpp:90-93): samples drawn from psi.psi_ref (a
+        PsiClassical's reference state), weights w |psi/psi_ref|^2, un-normalised sums; see `total_weight`.
+        `psi_sampling` (additive) overrides the sampling state, so any psi can be importance-sampled."""
+        if psi_sampling is None and not isinstance(psi, _PsiClassical):
+            raise TypeError("eval_with_psi_ref needs a PsiClassical (its reference state is sampled) or an explicit psi_sampling")
+        op = _match(operator, psi)
+        self._keep = (op, psi, ensemble, psi_sampling)
+        call("angpu_tdvp_eval_reweighted", self._h, op._h, psi._h, psi_sampling._h if psi_sampling is not None else None, ensemble._h)
 
     def _vec(self, name, n):
         out = np.empty(n, dtype=np.complex128)

@@ -238,6 +238,16 @@ int angpu_expectation_many(angpu_expval_t ev, unsigned num_ops, const angpu_oper
     for(unsigned i = 0; i < num_ops; i++) { out[2 * i] = h[4 * i]; out[2 * i + 1] = h[4 * i + 1]; }
     API_END
 }
+int angpu_expectation_reweighted(angpu_expval_t ev, angpu_operator_t op, angpu_psi_t psi, angpu_psi_t psi_sampling, angpu_ensemble_t ens, double out[2]) {
+    API_BEGIN NOTNULL(ev); NOTNULL(op); NOTNULL(psi); NOTNULL(psi_sampling); NOTNULL(ens); NOTNULL(out);
+    const cplx r = ev->ev.value_reweighted(*op->p, *psi->p, *psi_sampling->p, ens->e); out[0] = r.re; out[1] = r.im;
+    API_END
+}
+int angpu_exp_sigma_z(angpu_expval_t ev, angpu_operator_t op, angpu_psi_t psi, angpu_ensemble_t ens, double out[2]) {
+    API_BEGIN NOTNULL(ev); NOTNULL(op); NOTNULL(psi); NOTNULL(ens); NOTNULL(out);
+    const cplx r = ev->ev.exp_sigma_z(*op->p, *psi->p, ens->e); out[0] = r.re; out[1] = r.im;
+    API_END
+}
 int angpu_fluctuation(angpu_expval_t ev, angpu_operator_t op, angpu_psi_t psi, angpu_ensemble_t ens, double* fluctuation_out, double mean_out[2]) {
     API_BEGIN NOTNULL(ev); NOTNULL(op); NOTNULL(psi); NOTNULL(ens); NOTNULL(fluctuation_out); NOTNULL(mean_out);
     cplx m; ev->ev.fluctuation(*op->p, *psi->p, ens->e, *fluctuation_out, m); mean_out[0] = m.re; mean_out[1] = m.im;
@@ -256,6 +266,16 @@ int angpu_gradient(angpu_expval_t ev, angpu_operator_t op, angpu_psi_t psi, angp
 // ---- TDVP
 int angpu_tdvp_create(unsigned num_params, angpu_tdvp_t* out) { API_BEGIN NOTNULL(out); *out = new angpu_tdvp_s{std::unique_ptr<TDVP>(new TDVP(num_params))}; API_END }
 int angpu_tdvp_destroy(angpu_tdvp_t tdvp) { API_BEGIN delete tdvp; API_END }
+int angpu_tdvp_eval_reweighted(angpu_tdvp_t tdvp, angpu_operator_t op, angpu_psi_t psi, angpu_psi_t psi_sampling, angpu_ensemble_t ens) {
+    API_BEGIN NOTNULL(tdvp); NOTNULL(op); NOTNULL(psi); NOTNULL(ens);
+    Psi* sampling = psi_sampling ? psi_sampling->p.get() : nullptr;
+    if(!sampling) {
+        ANGPU_REQUIRE(psi->p->kind == Psi::CLASSICAL, "eval_with_psi_ref: psi_sampling may be NULL only for a PsiClassical (its psi_ref is used)");
+        sampling = static_cast<PsiClassical*>(psi->p.get())->sampling_ref();
+    }
+    tdvp->t->eval(*op->p, *psi->p, ens->e, true, sampling);
+    API_END
+}
 int angpu_tdvp_eval(angpu_tdvp_t tdvp, angpu_operator_t op, angpu_psi_t psi, angpu_ensemble_t ens) {
     API_BEGIN NOTNULL(tdvp); NOTNULL(op); NOTNULL(psi); NOTNULL(ens); tdvp->t->eval(*op->p, *psi->p, ens->e, true); API_END
 }

@@ -135,6 +135,14 @@ struct PsiClassical : Psi {
     std::vector<cplx> own_params;
     std::unique_ptr<PsiCNN> ref;        // null => PsiFullyPolarized
     DevBuf<OpDev> d_ops; DevBuf<cplx> d_params;
+    // the state eval_with_psi_ref samples from (kernel().psi_ref in the reference): the CNN, or for the FP variants a
+    // parameter-free PsiClassical with log psi = 0 (PsiFullyPolarized.hpp:41-49), created on first use
+    std::unique_ptr<PsiClassical> polarized;
+    Psi* sampling_ref() {
+        if(ref) return ref.get();
+        if(!polarized) polarized.reset(new PsiClassical(N, 1u, 0u, nullptr, nullptr, 0u, nullptr, cplx(0.0, 0.0)));
+        return polarized.get();
+    }
 
     PsiClassical(unsigned num_sites, unsigned order_, unsigned num_ops_, const Operator* const* ops_, const cplx* params_,
                  unsigned num_own, const PsiCNN* ref_, cplx lp_);

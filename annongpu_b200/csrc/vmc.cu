@@ -741,6 +741,21 @@ void Ensemble::generate(Psi& psi, SampleSet& S) {
         psi.log_psi(S, true);
     }
 }
+__global__ void k_reweight(double* __restrict__ w, const cplx* __restrict__ lp, const cplx* __restrict__ lp_sampling, size_t n) {
+    for(size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
+        w[k] *= exp(2.0 * (lp[k].re - lp_sampling[k].re));
+}
+void Ensemble::generate_reweighted(Psi& psi, Psi& psi_sampling, SampleSet& S) {
+    ANGPU_REQUIRE(psi.N == psi_sampling.N, "reweighting: psi and psi_sampling act on different numbers of sites");
+    generate(psi_sampling, S);
+    if(S.ns == 0) return;
+    lp_sampling.resize(S.ns);
+    ANGPU_CUDA(cudaMemcpyAsync(lp_sampling.p, S.log_psi.p, sizeof(cplx) * S.ns, cudaMemcpyDeviceToDevice, stream()));
+    S.has_angles = false;                       // any cached first-layer angles belong to psi_sampling
+    psi.log_psi(S, false);
+    k_reweight<<<grid_for(S.ns), 256, 0, stream()>>>(S.weight.p, S.log_psi.p, lp_sampling.p, S.ns);
+    ANGPU_CHECK_LAUNCH(); count_launch();
+}
 void Ensemble::acceptance(unsigned long long out[2]) {
     out[0] = out[1] = 0;
     if(d_acc_rej.n == 2) d_acc_rej.download(out, 2);
@@ -765,6 +780,37 @@ void ExpectationValue::fluctuation(const Operator& op, Psi& psi, Ensemble& ens, 
     double h[4]; d_scal.download(h, 4);
     mean = cplx(h[0], h[1]);
     fluct = std::sqrt(h[2] - abs2(mean));
+}
+
+cplx ExpectationValue::value_reweighted(const Operator& op, Psi& psi, Psi& psi_sampling, Ensemble& ens) {
+    ens.generate_reweighted(psi, psi_sampling, S);
+    psi.eloc(op, S);
+    d_scal.resize(8);
+    scalar_sums(S, true, false, d_scal.p, nullptr);
+    allreduce_sum(d_scal.p, 4);
+    double h[4]; d_scal.download(h, 4);
+    return cplx(h[0] / h[3], h[1] / h[3]);
+}
+// one warp per sample: eloc[s] = exp(sum over ALL strings of c_n <s|P_n|s'> coefficient)  (Operator.hpp:125-157)
+__global__ void k_exp_fast_energy(const OpDev op, const uint64_t* __restrict__ confs, size_t ns, cplx* __restrict__ out) {
+    const unsigned lane = threadIdx.x & 31u, wpb = blockDim.x >> 5;
+    for(size_t s = (size_t)blockIdx.x * wpb + (threadIdx.x >> 5); s < ns; s += (size_t)gridDim.x * wpb) {
+        const cplx e = fast_local_energy_warp(op, confs + s * op.words);
+        if(lane == 0) out[s] = cexp(e);
+    }
+}
+cplx ExpectationValue::exp_sigma_z(const Operator& op, Psi& psi, Ensemble& ens) {
+    ANGPU_REQUIRE(op.words == psi.words, "operator / wavefunction word count mismatch");
+    ens.generate(psi, S);
+    if(S.ns) {
+        k_exp_fast_energy<<<grid_for(S.ns * 32), 256, 0, stream()>>>(op.dev, S.conf.p, S.ns, S.eloc.p);
+        ANGPU_CHECK_LAUNCH(); count_launch();
+    }
+    d_scal.resize(8);
+    scalar_sums(S, true, false, d_scal.p, nullptr);
+    allreduce_sum(d_scal.p, 4);
+    double h[4]; d_scal.download(h, 4);
+    return cplx(h[0], h[1]);
 }
 
 // ============================================================================================ TDVP
@@ -839,11 +885,12 @@ void TDVP::mark(int i) {
 }
 TDVP::~TDVP() { for(auto& e : ev) if(e) cudaEventDestroy(e); }
 
-void TDVP::eval(const Operator& op, Psi& psi, Ensemble& ens, bool want_S) {
+void TDVP::eval(const Operator& op, Psi& psi, Ensemble& ens, bool want_S, Psi* psi_sampling) {
     ANGPU_REQUIRE(psi.P == P, "TDVP: num_params differs from the wavefunction's");
     last_psi = &psi; words = psi.words; num_steps_global = ens.num_steps();
     mark(0);
-    ens.generate(psi, S);
+    if(psi_sampling) ens.generate_reweighted(psi, *psi_sampling, S);
+    else ens.generate(psi, S);
     mark(1);
     psi.eloc(op, S);
     mark(2);

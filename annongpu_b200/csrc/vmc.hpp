@@ -42,6 +42,10 @@ struct Ensemble {
     }
     // fills S.conf / S.log_psi / S.weight for this process' share
     void generate(Psi& psi, SampleSet& S);
+    // importance reweighting (ExpectationValue.cu.template:127-172, TDVP.cu.template:15-74): configurations drawn from
+    // |psi_sampling|^2, then S.log_psi = log psi(s) and S.weight *= exp(2 (Re log psi(s) - Re log psi_sampling(s)))
+    void generate_reweighted(Psi& psi, Psi& psi_sampling, SampleSet& S);
+    DevBuf<cplx> lp_sampling;
     void acceptance(unsigned long long out[2]);
 };
 
@@ -52,6 +56,11 @@ struct ExpectationValue {
     cplx value(const Operator& op, Psi& psi, Ensemble& ens);
     // (sqrt(<|A_loc|^2> - |<A>|^2), <A>)  (:176-216)
     void fluctuation(const Operator& op, Psi& psi, Ensemble& ens, double& fluct, cplx& mean);
+    // sum_s w_s r_s A_loc(s) / sum_s w_s r_s with samples from psi_sampling (ExpectationValue.cu.template:127-172; the
+    // reference never accumulates its denominator `prob_ratio`, i.e. divides by zero -- the evident intent is implemented)
+    cplx value_reweighted(const Operator& op, Psi& psi, Psi& psi_sampling, Ensemble& ens);
+    // sum_s w_s exp(fast_local_energy(op, s))  (ExpectationValue.cu.template:52-82)
+    cplx exp_sigma_z(const Operator& op, Psi& psi, Ensemble& ens);
 };
 
 struct TDVP {
@@ -75,7 +84,9 @@ struct TDVP {
     explicit TDVP(unsigned P_) : P(P_) {}
     const cplx* Ok_dev() const { return packed.p + 2; }
     // TDVP::eval (TDVP.cu.template:182-302): E, E2, <O_k>, F, O_k_samples, S.
-    void eval(const Operator& op, Psi& psi, Ensemble& ens, bool want_S);
+    // psi_sampling != null: TDVP::eval(..., true_t) = eval_with_psi_ref (TDVP.cu.template:15-74): samples from psi_sampling,
+    // weights multiplied by |psi/psi_sampling|^2 and NOT normalised (total_weight is exposed, as in the reference)
+    void eval(const Operator& op, Psi& psi, Ensemble& ens, bool want_S, Psi* psi_sampling = nullptr);
     // TDVP::eval_F_vector (:306-334).  For PsiRBM the samples are kept in factorised form unless dense rows are requested.
     void eval_F(const Operator& op, Psi& psi, Ensemble& ens) { eval(op, psi, ens, false); }
     double var_H() const { return E2 - abs2(E); }

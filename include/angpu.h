@@ -138,6 +138,13 @@ int angpu_expval_destroy(angpu_expval_t ev);
 int angpu_expectation(angpu_expval_t ev, angpu_operator_t op, angpu_psi_t psi, angpu_ensemble_t ens, double out[2]);     /* :20-50 */
 int angpu_expectation_many(angpu_expval_t ev, unsigned num_ops, const angpu_operator_t* ops, angpu_psi_t psi,
                            angpu_ensemble_t ens, double* out);                                                            /* :81-130 */
+/* importance-reweighted <A>: configurations from |psi_sampling|^2, weights times |psi/psi_sampling|^2, result normalised
+ * by the summed weights (operator()(op, psi, psi_sampling, ens), :127-172; the reference divides by a never-accumulated
+ * `prob_ratio`, i.e. by zero -- the intended quotient is returned here) */
+int angpu_expectation_reweighted(angpu_expval_t ev, angpu_operator_t op, angpu_psi_t psi, angpu_psi_t psi_sampling,
+                                 angpu_ensemble_t ens, double out[2]);
+/* sum_s w_s exp(sum_n c_n <s|P_n|s'>_coefficient)  (exp_sigma_z, :52-82; Operator.hpp:138-157) */
+int angpu_exp_sigma_z(angpu_expval_t ev, angpu_operator_t op, angpu_psi_t psi, angpu_ensemble_t ens, double out[2]);
 int angpu_fluctuation(angpu_expval_t ev, angpu_operator_t op, angpu_psi_t psi, angpu_ensemble_t ens,
                       double* fluctuation_out, double mean_out[2]);                                                       /* :176-216 */
 int angpu_gradient(angpu_expval_t ev, angpu_operator_t op, angpu_psi_t psi, angpu_ensemble_t ens,
@@ -148,6 +155,11 @@ int angpu_tdvp_create(unsigned num_params, angpu_tdvp_t* out);
 int angpu_tdvp_destroy(angpu_tdvp_t tdvp);
 int angpu_tdvp_eval(angpu_tdvp_t tdvp, angpu_operator_t op, angpu_psi_t psi, angpu_ensemble_t ens);    /* eval, :182-302 */
 int angpu_tdvp_eval_F(angpu_tdvp_t tdvp, angpu_operator_t op, angpu_psi_t psi, angpu_ensemble_t ens);  /* eval_F_vector, :306-334 */
+/* eval_with_psi_ref = TDVP::eval(..., true_t) (TDVP.hpp:90-93, TDVP.cu.template:15-74): samples from psi_sampling (the
+ * reference passes psi.psi_ref of a PsiClassical), weights w_s |psi(s)/psi_sampling(s)|^2, sums NOT normalised;
+ * total_weight (angpu_tdvp_get_scalars) = sum of those weights for THIS call (the reference never clears it).
+ * psi_sampling == NULL: psi must be a PsiClassical and its own reference state is used. */
+int angpu_tdvp_eval_reweighted(angpu_tdvp_t tdvp, angpu_operator_t op, angpu_psi_t psi, angpu_psi_t psi_sampling, angpu_ensemble_t ens);
 int angpu_tdvp_get_S(angpu_tdvp_t tdvp, double* out);                 /* S_matrix [P][P] row-major */
 int angpu_tdvp_get_F(angpu_tdvp_t tdvp, double* out);                 /* F_vector */
 int angpu_tdvp_get_O_k(angpu_tdvp_t tdvp, double* out);               /* O_k_ar */

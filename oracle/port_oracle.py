@@ -328,6 +328,19 @@ def _samples_and_weights(psi, ens):
     return confs, lp, np.full(len(confs), 1.0 / ens.num_samples)
 
 
+def _reweighted(psi, psi_sampling, ens):
+    """Configurations from |psi_sampling|^2, weights w |psi/psi_sampling|^2 (ExpectationValue.cu.template:127-172,
+    TDVP.cu.template:28-59)."""
+    confs, lp_s, w = _samples_and_weights(psi_sampling, ens)
+    lp, _, _ = eval_samples(psi, None, confs)
+    return confs, lp, w * np.exp(2.0 * (lp.real - lp_s.real))
+
+
+def fully_polarized(num_sites):
+    """PsiFullyPolarized (include/quantum_state/PsiFullyPolarized.hpp:41-49): log psi = 0, no parameters."""
+    return PsiClassical(num_sites, 1, [], np.zeros(0, dtype=complex), None, 0.0)
+
+
 # ---------------------------------------------------------------- network functions (reductions in numpy)
 
 def psi_vector(psi, ens):
@@ -365,6 +378,24 @@ def expectation(op, psi, ens):
     return complex(np.sum(w * el))
 
 
+def expectation_reweighted(op, psi, psi_sampling, ens):
+    """The evident intent of ExpectationValue::operator()(op, psi, psi_sampling, ens) (:127-172); the reference itself
+    never accumulates its denominator."""
+    confs, _, w = _reweighted(psi, psi_sampling, ens)
+    _, el, _ = eval_samples(psi, op, confs)
+    return complex(np.sum(w * el) / np.sum(w))
+
+
+def exp_sigma_z(op, psi, ens):
+    """sum_s w_s exp(fast_local_energy(s)) (ExpectationValue.cu.template:52-82, Operator.hpp:123-136)."""
+    confs, _, w = _samples_and_weights(psi, ens)
+    e = np.zeros(len(confs), dtype=complex)
+    for s, conf in enumerate(confs):
+        for n in range(op.num_strings):
+            e[s] += op.coeffs[n] * op.pauli_apply(n, conf)[0]
+    return complex(np.sum(w * np.exp(e)))
+
+
 def fluctuation(op, psi, ens):
     confs, _, w = _samples_and_weights(psi, ens)
     _, el, _ = eval_samples(psi, op, confs)
@@ -384,8 +415,9 @@ class TDVP:
     def __init__(self, num_params):
         self.P = int(num_params)
 
-    def eval(self, op, psi, ens, want_S=True):
-        confs, _, w = _samples_and_weights(psi, ens)
+    def eval(self, op, psi, ens, want_S=True, psi_sampling=None):
+        confs, _, w = _samples_and_weights(psi, ens) if psi_sampling is None else _reweighted(psi, psi_sampling, ens)
+        self.total_weight = float(np.sum(w))
         _, el, O = eval_samples(psi, op, confs, want_O=True)
         self.confs, self.E_loc_samples = confs, el
         self.O_k_samples, self.weight_samples = O, w
@@ -399,6 +431,12 @@ class TDVP:
 
     def eval_F(self, op, psi, ens):
         self.eval(op, psi, ens, want_S=False)
+
+    def eval_with_psi_ref(self, op, psi, ens, psi_sampling=None):
+        """TDVP::eval(..., true_t) (TDVP.cu.template:15-74): samples from psi's reference state, un-normalised sums."""
+        if psi_sampling is None:
+            psi_sampling = psi._ref if psi._ref is not None else fully_polarized(psi.num_sites)
+        self.eval(op, psi, ens, want_S=True, psi_sampling=psi_sampling)
 
     def S_dot_vector(self, vec, ens=None):
         vec = _c128(vec)

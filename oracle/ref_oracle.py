@@ -78,6 +78,9 @@ def lib():
         L.ref_tdvp_get.argtypes = [vp, vp, vp, vp, vp]
         L.ref_tdvp_get_samples.argtypes = [vp, vp, vp]
         L.ref_tdvp_S_dot_vector.argtypes = [vp, vp, i32, vp, vp]
+        L.ref_exp_sigma_z.argtypes = [i32, vp, vp, i32, vp, vp]
+        L.ref_tdvp_eval_with_psi_ref.argtypes = [vp, i32, vp, vp, i32, vp]
+        L.ref_tdvp_eval_with_psi_ref.restype = dbl
         L.ref_set_gpu.argtypes = [i32]
         L.ref_device_synchronize.restype = i32
         _lib = L
@@ -329,6 +332,12 @@ def fluctuation(op, psi, ens):
     return float(out[0]), complex(out[1], out[2])
 
 
+def exp_sigma_z(op, psi, ens):
+    out = np.empty(2)
+    lib().ref_exp_sigma_z(psi.kind, psi.h, op.h, ens.kind, ens.h, _p(out))
+    return complex(out[0], out[1])
+
+
 def gradient(op, psi, ens):
     g, e = _cout(psi.num_params), _cout(1)
     lib().ref_gradient(psi.kind, psi.h, op.h, ens.kind, ens.h, _p(g), _p(e))
@@ -347,6 +356,12 @@ class TDVP:
     def eval(self, op, psi, ens):
         self._ns = ens.num_steps
         lib().ref_tdvp_eval(self.h, psi.kind, psi.h, op.h, ens.kind, ens.h)
+
+    def eval_with_psi_ref(self, op, psi, ens):
+        """TDVP::eval(..., true_t) (PsiClassical kinds only); returns total_weight of this call."""
+        self._ns = ens.num_steps
+        self.total_weight = float(lib().ref_tdvp_eval_with_psi_ref(self.h, psi.kind, psi.h, op.h, ens.kind, ens.h))
+        return self.total_weight
 
     def eval_F(self, op, psi, ens):
         self._ns = ens.num_steps

@@ -106,6 +106,16 @@ void with_psi(int kind, void* h, F f) {
 }
 
 template<typename F>
+void with_classical(int kind, void* h, F f) {
+    switch(kind) {
+        case CLFP1:  f(*static_cast<PsiClassicalFP<1u>*>(h)); break;
+        case CLFP2:  f(*static_cast<PsiClassicalFP<2u>*>(h)); break;
+        case CLANN1: f(*static_cast<PsiClassicalANN<1u>*>(h)); break;
+        case CLANN2: f(*static_cast<PsiClassicalANN<2u>*>(h)); break;
+    }
+}
+
+template<typename F>
 void with_ens(int kind, void* h, F f) {
     if(kind == ES) f(*static_cast<ExactSummationSpins*>(h));
     else           f(*static_cast<MonteCarloSpins*>(h));
@@ -311,6 +321,12 @@ void ref_fluctuation(int kind, void* h, void* op, int ek, void* e, double* out) 
         });
     });
 }
+void ref_exp_sigma_z(int kind, void* h, void* op, int ek, void* e, double* out) {
+    ExpectationValue ev(g_gpu);
+    with_psi(kind, h, [&](auto& psi) {
+        with_ens(ek, e, [&](auto& ens) { store(out, ev.exp_sigma_z(*static_cast<Operator*>(op), psi, ens)); });
+    });
+}
 void ref_gradient(int kind, void* h, void* op, int ek, void* e, double* grad_out, double* E_out) {
     ExpectationValue ev(g_gpu);
     with_psi(kind, h, [&](auto& psi) {
@@ -330,6 +346,17 @@ void ref_tdvp_eval(void* t, int kind, void* h, void* op, int ek, void* e) {
     with_psi(kind, h, [&](auto& psi) {
         with_ens(ek, e, [&](auto& ens) { static_cast<TDVP*>(t)->eval(*static_cast<Operator*>(op), psi, ens, false_t()); });
     });
+}
+// TDVP::eval(..., true_t) = eval_with_psi_ref (TDVP.hpp:90-93): PsiClassical kinds only.  total_weight is never cleared by
+// the reference (TDVP.cu.template:206), so it is zeroed here before the call and returned.
+double ref_tdvp_eval_with_psi_ref(void* t, int kind, void* h, void* op, int ek, void* e) {
+    auto& tdvp = *static_cast<TDVP*>(t);
+    tdvp.total_weight.clear();
+    with_classical(kind, h, [&](auto& psi) {
+        with_ens(ek, e, [&](auto& ens) { tdvp.eval(*static_cast<Operator*>(op), psi, ens, true_t()); });
+    });
+    tdvp.total_weight.update_host();
+    return tdvp.total_weight.front();
 }
 void ref_tdvp_eval_F(void* t, int kind, void* h, void* op, int ek, void* e) {
     with_psi(kind, h, [&](auto& psi) {

@@ -47,6 +47,7 @@ def record(out, name, psi, H, N):
     out[f"{name}/psi_vector_head"] = R.psi_vector(psi, es)[:64]
     out[f"{name}/apply_operator_head"] = R.apply_operator(psi, op, es)[:64]
     out[f"{name}/log_psi_mean"] = R.log_psi(psi, es)
+    out[f"{name}/exp_sigma_z"] = R.exp_sigma_z(op, psi, es)
 
 
 def main():
@@ -56,6 +57,11 @@ def main():
     for name, (N, order, Hl, pr, ref_spec, lp, H) in classical_zoo().items():
         psi = make_classical(R, N, order, Hl, pr, ref_spec, lp)
         record(out, name, psi, H, N)
+        # TDVP::eval(..., true_t) = eval_with_psi_ref: samples from the classical state's reference state
+        t = R.TDVP(psi.num_params)
+        out[f"{name}/wref/total_weight"] = t.eval_with_psi_ref(make_op(R, H), psi, R.ExactSummation(N))
+        out[f"{name}/wref/E"], out[f"{name}/wref/F"], out[f"{name}/wref/Ok"] = t.E_local, t.F_vector, t.O_k_vector
+        out[f"{name}/wref/S"] = t.S_matrix
     # primitives: Pauli action (bit-exact) and activation polynomials
     rng = np.random.default_rng(7)
     a, b, c = (rng.integers(0, 1 << 63, size=64, dtype=np.uint64) for _ in range(3))

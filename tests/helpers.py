@@ -119,6 +119,9 @@ class GpuAdapter:
     def gradient(self, op, psi, ens):
         return self.ev.gradient(op, psi, ens)
 
+    def exp_sigma_z(self, op, psi, ens):
+        return self.ev.exp_sigma_z(op, psi, ens)
+
     def TDVP(self, P):
         return self.A.TDVP(P, True)
 

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 from helpers import GpuAdapter, classical_zoo, make_classical, make_psi, zoo
-from test_oracle_pinned import GOLDEN, check_against_golden
+from test_oracle_pinned import GOLDEN, check_against_golden, check_wref_against_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -19,7 +19,9 @@ def test_gpu_matches_reference_golden(gpu, name):
 def test_gpu_matches_reference_golden_classical(gpu, name):
     N, order, Hl, pr, ref_spec, lp, H = classical_zoo()[name]
     ad = GpuAdapter(gpu)
-    check_against_golden(ad, name, make_classical(gpu, N, order, Hl, pr, ref_spec, lp), H, N, ad.ExactSummation)
+    psi = make_classical(gpu, N, order, Hl, pr, ref_spec, lp)
+    check_against_golden(ad, name, psi, H, N, ad.ExactSummation)
+    check_wref_against_golden(ad, name, psi, H, N, ad.ExactSummation)
 
 
 def test_gpu_primitives_match_golden(gpu):

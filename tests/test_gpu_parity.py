@@ -396,3 +396,58 @@ def test_deep_block_sampler_matches_generic_at_c4_shape(gpu):
     assert np.array_equal(out["block"][0], out["generic"][0])
     assert rel_err(out["block"][1], out["generic"][1]) <= 1e-10
     assert out["block"][2] == out["generic"][2]
+
+
+# ------------------------------------------------------------------------------------------------ SURVEY 8f rank 2
+
+def test_reweighted_expectation_and_exp_sigma_z(gpu, port):
+    """ExpectationValue(op, psi, psi_sampling, ens) and exp_sigma_z against the oracle: exact summation within 1e-10,
+    Monte Carlo on identical chains (same Philox stream) within 1e-9."""
+    specA, H, N = zoo()["rbm10"]
+    specB = F.rbm_spec(10, 20, noise=4e-2, final_weight=8, seed=31)
+    ev = gpu.ExpectationValue(True)
+    pg, sg, og = make_psi(gpu, specA), make_psi(gpu, specB), make_op(gpu, H)
+    pp, sp, op_ = make_psi(port, specA), make_psi(port, specB), make_op(port, H)
+    eg, ep = gpu.ExactSummationSpins(N), port.ExactSummation(N)
+    r_p = port.expectation_reweighted(op_, pp, sp, ep)
+    assert abs(ev(og, pg, sg, eg) - r_p) <= TOL * max(1.0, abs(r_p))
+    # reweighting with exact summation must reproduce the normalised direct expectation value
+    direct = port.expectation(op_, pp, ep) / port.psi_norm(pp, ep) ** 2
+    assert abs(ev(og, pg, sg, eg) - direct) <= 1e-9 * max(1.0, abs(direct))
+    z_p = port.exp_sigma_z(op_, pp, ep)
+    assert abs(ev.exp_sigma_z(og, pg, eg) - z_p) <= TOL * abs(z_p)
+    mg, mp = gpu.MonteCarloSpins(512, 2, 5, 64, True, seed=77), port.MonteCarlo(512, 2, 5, 64, seed=77)
+    r_p = port.expectation_reweighted(op_, pp, sp, mp)
+    assert abs(ev(og, pg, sg, mg) - r_p) <= 1e-9 * max(1.0, abs(r_p))
+    z_p = port.exp_sigma_z(op_, pp, mp)
+    assert abs(ev.exp_sigma_z(og, pg, mg) - z_p) <= 1e-9 * abs(z_p)
+
+
+@pytest.mark.parametrize("name", sorted(classical_zoo()))
+def test_eval_with_psi_ref_matches_oracle(gpu, port, name):
+    """TDVP.eval_with_psi_ref (samples from the classical state's reference, un-normalised reweighted sums)."""
+    N, order, Hl, pr, ref_spec, lp, H = classical_zoo()[name]
+    pg, pp = make_classical(gpu, N, order, Hl, pr, ref_spec, lp), make_classical(port, N, order, Hl, pr, ref_spec, lp)
+    og, op_ = make_op(gpu, H), make_op(port, H)
+    for eg, ep, tol in ((gpu.ExactSummationSpins(N), port.ExactSummation(N), TOL),
+                        (gpu.MonteCarloSpins(256, 1, 4, 32, True, seed=5), port.MonteCarlo(256, 1, 4, 32, seed=5), 1e-9)):
+        tg, tp = gpu.TDVP(pg.num_params, True), port.TDVP(pp.num_params)
+        tg.eval_with_psi_ref(og, pg, eg)
+        tp.eval_with_psi_ref(op_, pp, ep)
+        assert abs(tg.total_weight - tp.total_weight) <= tol * tp.total_weight
+        assert abs(tg.E_local - tp.E_local) <= tol * max(1.0, abs(tp.E_local))
+        assert rel_err(tg.F_vector, tp.F_vector) <= tol and rel_err(tg.O_k_vector, tp.O_k_vector) <= tol
+        assert rel_err(tg.S_matrix, tp.S_matrix) <= tol
+
+
+def test_eval_with_explicit_sampling_state(gpu, port):
+    """Additive: any psi can be importance-sampled from another (here PsiDeep from a PsiRBM)."""
+    spec, H, N = zoo()["deep2"]
+    samp = F.rbm_spec(8, 16, noise=3e-2, final_weight=2, seed=41)
+    pg, sg, og = make_psi(gpu, spec), make_psi(gpu, samp), make_op(gpu, H)
+    pp, sp, op_ = make_psi(port, spec), make_psi(port, samp), make_op(port, H)
+    tg, tp = gpu.TDVP(pg.num_params, True), port.TDVP(pp.num_params)
+    tg.eval_with_psi_ref(og, pg, gpu.ExactSummationSpins(N), psi_sampling=sg)
+    tp.eval_with_psi_ref(op_, pp, port.ExactSummation(N), psi_sampling=sp)
+    assert rel_err(tg.S_matrix, tp.S_matrix) <= TOL and rel_err(tg.F_vector, tp.F_vector) <= TOL
+    assert abs(tg.total_weight - tp.total_weight) <= TOL * tp.total_weight

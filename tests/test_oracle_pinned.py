@@ -36,6 +36,19 @@ def check_against_golden(mod, name, psi, H, N, ensemble_cls):
     assert rel_err(mod.psi_vector(psi, es)[:64], g("psi_vector_head")) <= TOL
     assert rel_err(mod.apply_operator(psi, op, es)[:64], g("apply_operator_head")) <= TOL
     assert abs(mod.log_psi(psi, es) - g("log_psi_mean")) <= 1e-9
+    if hasattr(mod, "exp_sigma_z"):
+        assert abs(mod.exp_sigma_z(op, psi, es) - g("exp_sigma_z")) <= TOL * abs(g("exp_sigma_z"))
+
+
+def check_wref_against_golden(mod, name, psi, H, N, ensemble_cls):
+    """TDVP::eval(..., true_t) = eval_with_psi_ref of a PsiClassical, after check_against_golden fixed its log_prefactor."""
+    g = lambda k: GOLDEN[f"{name}/wref/{k}"]   # noqa: E731
+    t = mod.TDVP(psi.num_params)
+    t.eval_with_psi_ref(make_op(mod, H), psi, ensemble_cls(N))
+    assert abs(t.total_weight - g("total_weight")) <= TOL * g("total_weight")
+    assert abs(t.E_local - g("E")) <= TOL * max(1.0, abs(g("E")))
+    assert rel_err(t.F_vector, g("F")) <= TOL and rel_err(t.O_k_vector, g("Ok")) <= TOL
+    assert rel_err(t.S_matrix, g("S")) <= TOL
 
 
 @pytest.mark.parametrize("name", sorted(zoo()))
@@ -47,7 +60,9 @@ def test_port_matches_reference_golden(port, name):
 @pytest.mark.parametrize("name", sorted(classical_zoo()))
 def test_port_matches_reference_golden_classical(port, name):
     N, order, Hl, pr, ref_spec, lp, H = classical_zoo()[name]
-    check_against_golden(port, name, make_classical(port, N, order, Hl, pr, ref_spec, lp), H, N, port.ExactSummation)
+    psi = make_classical(port, N, order, Hl, pr, ref_spec, lp)
+    check_against_golden(port, name, psi, H, N, port.ExactSummation)
+    check_wref_against_golden(port, name, psi, H, N, port.ExactSummation)
 
 
 def test_port_primitives_match_golden(port):

@@ -34,8 +34,30 @@ def case(name, scale):
     from oracle import ref_oracle as R
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import helpers
-    R.set_gpu(True)
     out = {"case": name}
+    # the reference's serial host path (gpu=false) on a bounded sample of the same workload, one core
+    R.set_gpu(False)
+    if name == "C1":
+        spec, H = F.config_C1()
+        rp, ro, re_ = helpers.make_psi(R, spec), helpers.make_op(R, H), R.ExactSummation(16)
+        out["ref_cpu_ms"] = wall(lambda: R.gradient(ro, rp, re_), 1)
+        out["ref_cpu_unit"] = "ms per call (65536 states), 1 core"
+    elif name == "C2_M128":
+        N, M = 64, 128
+        spec, H = F.rbm_spec(N, M, noise=0.02 / np.sqrt(2.0), final_weight=1.0, seed=1234), F.heisenberg(N, F.ring_bonds(N))
+        rp, ro, rm = helpers.make_psi(R, spec), helpers.make_op(R, H), R.MonteCarlo(256, 1, 10, 1)
+        rt = R.TDVP(rp.num_params)
+        ms = wall(lambda: rt.eval_F(ro, rp, rm), 1)
+        out["ref_cpu_samples_per_s"] = 256 / (ms * 1e-3)
+        out["ref_cpu_unit"] = "MonteCarloSpins(256, 1, 10, 1) on 1 core: one chain, 10 thermalisation sweeps once + 1 sweep per sample"
+    elif name == "C4":
+        spec, H = F.config_C4()
+        rp, ro, rm = helpers.make_psi(R, spec), helpers.make_op(R, H), R.MonteCarlo(32, 1, 10, 1)
+        rt = R.TDVP(rp.num_params)
+        ms = wall(lambda: rt.eval(ro, rp, rm), 1)
+        out["ref_cpu_samples_per_s"] = 32 / (ms * 1e-3)
+        out["ref_cpu_unit"] = "TDVP.eval with MonteCarloSpins(32, 1, 10, 1) on 1 core (S fill is O(Ns P^2) on the host)"
+    R.set_gpu(True)
     if name == "C1":
         spec, H = F.config_C1()
         rp, ro, re_ = helpers.make_psi(R, spec), helpers.make_op(R, H), R.ExactSummation(16)
