@@ -81,6 +81,10 @@ _SIGNATURES = {
     "angpu_tdvp_destroy": [vp],
     "angpu_tdvp_eval": [vp, vp, vp, vp],
     "angpu_tdvp_eval_F": [vp, vp, vp, vp],
+    "angpu_hsd_create": [u32, vp],
+    "angpu_hsd_destroy": [vp],
+    "angpu_hsd_distance": [vp, vp, vp, vp, C.c_int, vp, vp],
+    "angpu_hsd_gradient": [vp, vp, vp, vp, C.c_int, vp, C.c_float, vp, vp],
     "angpu_tdvp_eval_reweighted": [vp, vp, vp, vp, vp],
     "angpu_tdvp_get_S": [vp, vp],
     "angpu_tdvp_get_F": [vp, vp],

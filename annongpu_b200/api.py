@@ -26,6 +26,7 @@ from .factories import PauliSum, masks_to_words, words_for
 __all__ = [
     "PsiRBM", "PsiDeep", "PsiCNN", "PsiClassicalFP_1", "PsiClassicalFP_2", "PsiClassicalANN_1", "PsiClassicalANN_2",
     "PsiFullyPolarized", "Operator", "Spins", "MonteCarloSpins", "ExactSummationSpins", "ExpectationValue", "TDVP",
+    "HilbertSpaceDistance",
     "log_psi_s", "psi_O_k", "psi_O_k_vector", "log_psi", "psi_vector", "log_psi_vector", "apply_operator",
     "local_energies", "activation_function", "pauli_apply", "setDevice", "start_profiling", "stop_profiling",
     "synchronize", "launch_count", "set_stream", "measure_fp64_tflops",
@@ -621,6 +622,37 @@ class ExpectationValue:
     def gradient_with_noise(self, operator, psi, ensemble):
         raise NotImplementedError("gradient_with_noise: the reference's body is commented out and returns uninitialised "
                                   "arrays (ExpectationValue.cu.template:276-333); there is nothing to reproduce")
+
+
+class HilbertSpaceDistance:
+    """HilbertSpaceDistance(num_params, gpu) (pyANNonGPU/main.cpp.template:436-440): ``hsd(psi, psi_prime, operator,
+    is_unitary, ensemble) -> distance`` and ``hsd.gradient(psi, psi_prime, operator, is_unitary, ensemble, nu) ->
+    (gradient[num_params of psi_prime], distance)``.  The reference binds it for (PsiDeep, PsiDeep) and (PsiCNN, PsiCNN);
+    here any pair of models on the same lattice works."""
+
+    def __init__(self, num_params, gpu=True):
+        _require_gpu(gpu)
+        self.num_params = int(num_params)
+        self._h = C.c_void_p()
+        call("angpu_hsd_create", self.num_params, C.byref(self._h))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.angpu_hsd_destroy(self._h)
+            self._h = None
+
+    def __call__(self, psi, psi_prime, operator_, is_unitary, spin_ensemble):
+        op = _match(operator_, psi)
+        d = C.c_double()
+        call("angpu_hsd_distance", self._h, psi._h, psi_prime._h, op._h, int(bool(is_unitary)), spin_ensemble._h, C.byref(d))
+        return float(d.value)
+
+    def gradient(self, psi, psi_prime, operator_, is_unitary, spin_ensemble, nu):
+        op = _match(operator_, psi)
+        g, d = np.empty(self.num_params, dtype=np.complex128), C.c_double()
+        call("angpu_hsd_gradient", self._h, psi._h, psi_prime._h, op._h, int(bool(is_unitary)), spin_ensemble._h, float(nu),
+             _p(g), C.byref(d))
+        return g, float(d.value)
 
 
 class TDVP:

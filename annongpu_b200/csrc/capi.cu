@@ -13,6 +13,7 @@ struct angpu_operator_s { std::unique_ptr<Operator> p; };
 struct angpu_ensemble_s { Ensemble e; };
 struct angpu_expval_s   { ExpectationValue ev; std::unique_ptr<TDVP> grad; };
 struct angpu_tdvp_s     { std::unique_ptr<TDVP> t; };
+struct angpu_hsd_s      { std::unique_ptr<HilbertSpaceDistance> h; };
 
 static thread_local std::string g_err;
 
@@ -260,6 +261,21 @@ int angpu_gradient(angpu_expval_t ev, angpu_operator_t op, angpu_psi_t psi, angp
     ev->grad->eval_F(*op->p, *psi->p, ens->e);
     ev->grad->F.download(cp(gradient_out), psi->p->P);
     mean_out[0] = ev->grad->E.re; mean_out[1] = ev->grad->E.im;
+    API_END
+}
+
+// ---- HilbertSpaceDistance
+int angpu_hsd_create(unsigned num_params, angpu_hsd_t* out) { API_BEGIN NOTNULL(out); *out = new angpu_hsd_s{std::unique_ptr<HilbertSpaceDistance>(new HilbertSpaceDistance(num_params))}; API_END }
+int angpu_hsd_destroy(angpu_hsd_t hsd) { API_BEGIN delete hsd; API_END }
+int angpu_hsd_distance(angpu_hsd_t hsd, angpu_psi_t psi, angpu_psi_t psi_prime, angpu_operator_t op, int is_unitary, angpu_ensemble_t ens, double* distance_out) {
+    API_BEGIN NOTNULL(hsd); NOTNULL(psi); NOTNULL(psi_prime); NOTNULL(op); NOTNULL(ens); NOTNULL(distance_out);
+    *distance_out = hsd->h->distance(*psi->p, *psi_prime->p, *op->p, is_unitary != 0, ens->e);
+    API_END
+}
+int angpu_hsd_gradient(angpu_hsd_t hsd, angpu_psi_t psi, angpu_psi_t psi_prime, angpu_operator_t op, int is_unitary, angpu_ensemble_t ens,
+                       float nu, double* gradient_out, double* distance_out) {
+    API_BEGIN NOTNULL(hsd); NOTNULL(psi); NOTNULL(psi_prime); NOTNULL(op); NOTNULL(ens); NOTNULL(gradient_out); NOTNULL(distance_out);
+    *distance_out = hsd->h->gradient(cp(gradient_out), *psi->p, *psi_prime->p, *op->p, is_unitary != 0, ens->e, nu);
     API_END
 }
 

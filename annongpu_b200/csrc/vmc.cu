@@ -896,16 +896,7 @@ void TDVP::eval(const Operator& op, Psi& psi, Ensemble& ens, bool want_S, Psi* p
     mark(2);
     packed.resize(2 + 2 * (size_t)P);
     scalar_sums(S, true, false, reinterpret_cast<double*>(packed.p), nullptr);
-    have_S = false;
-    if(psi.kind == Psi::RBM && !want_S) {
-        PsiRBM& rbm = static_cast<PsiRBM&>(psi);
-        rbm.compute_T(S, T);
-        factorised = true; have_dense_O = false; rbm_N = rbm.N; rbm_M = rbm.M;
-    } else {
-        O.resize(S.ns * (size_t)P);
-        psi.ok_rows(S, 0, S.ns, O.p);
-        factorised = false; have_dense_O = true;
-    }
+    prepare_rows(psi, want_S);
     col_reduce(*this, S.eloc.p, packed.p + 2, packed.p + 2 + P);
     allreduce_sum(reinterpret_cast<double*>(packed.p), 2 * (2 + 2 * (size_t)P));
     mark(3);
@@ -923,6 +914,22 @@ void TDVP::eval(const Operator& op, Psi& psi, Ensemble& ens, bool want_S, Psi* p
     }
     if(want_S) build_S();
 }
+
+void TDVP::prepare_rows(Psi& psi, bool dense) {
+    ANGPU_REQUIRE(psi.P == P, "TDVP: num_params differs from the wavefunction's");
+    last_psi = &psi; words = psi.words;
+    have_S = false;
+    if(psi.kind == Psi::RBM && !dense) {
+        PsiRBM& rbm = static_cast<PsiRBM&>(psi);
+        rbm.compute_T(S, T);
+        factorised = true; have_dense_O = false; rbm_N = rbm.N; rbm_M = rbm.M;
+    } else {
+        O.resize(S.ns * (size_t)P);
+        psi.ok_rows(S, 0, S.ns, O.p);
+        factorised = false; have_dense_O = true;
+    }
+}
+void TDVP::weighted_conj_column_sums(const cplx* X, cplx* x_out) { col_reduce(*this, X, nullptr, x_out); }
 
 void TDVP::ensure_dense_O(Psi* psi) {
     if(have_dense_O) return;
@@ -1138,6 +1145,72 @@ void TDVP::solve_dense(double shift_abs, double shift_rel, cplx rhs_phase, cplx*
     mark(6);
     b.download(x_host, n);
     if(profile) ANGPU_CUDA(cudaEventElapsedTime(&phase_ms[5], ev[5], ev[6]));
+}
+
+// ============================================================================================ HilbertSpaceDistance
+// per sample (HilbertSpaceDistance.cu.template:41-70): omega, probability ratio, next-state norm; block sums of
+// w*omega (2), w*ratio, w*norm into out[4] by a single block (fixed order: deterministic)
+__global__ void __launch_bounds__(RED_T) k_hsd_terms(const double* __restrict__ w, const cplx* __restrict__ lp, const cplx* __restrict__ lpp,
+        const cplx* __restrict__ eloc, size_t ns, bool is_unitary, cplx* __restrict__ omega_out, cplx* __restrict__ ratio_out, double* __restrict__ out4) {
+    double v[4] = {0.0, 0.0, 0.0, 0.0}, red[4];
+    for(size_t s = threadIdx.x; s < ns; s += RED_T) {
+        const cplx d = conj(lpp[s] - lp[s]), E = eloc[s];
+        cplx om; double nsn;
+        if(is_unitary) { om = cexp(d) * E; nsn = abs2(E); }
+        else           { om = cexp(E + d); nsn = exp(2.0 * E.re); }
+        const double r = exp(2.0 * (lpp[s].re - lp[s].re));
+        omega_out[s] = om; ratio_out[s] = cplx(r, 0.0);
+        v[0] += w[s] * om.re; v[1] += w[s] * om.im; v[2] += w[s] * r; v[3] += w[s] * nsn;
+    }
+    block_reduce<4>(v, red);
+    if(threadIdx.x == 0) { out4[0] = red[0]; out4[1] = red[1]; out4[2] = red[2]; out4[3] = red[3]; }
+}
+
+void HilbertSpaceDistance::averages(Psi& psi, Psi& psi_prime, const Operator& op, bool is_unitary, Ensemble& ens, bool want_gradient, double h[5]) {
+    ANGPU_REQUIRE(psi.N == psi_prime.N, "HilbertSpaceDistance: psi and psi_prime act on different numbers of sites");
+    ANGPU_REQUIRE(psi_prime.P == P, "HilbertSpaceDistance: num_params differs from psi_prime's");
+    ens.generate(psi, S);
+    psi.eloc(op, S);
+    SampleSet& Sp = rows.S;                            // the same configurations and weights, log psi' and psi' caches
+    Sp.resize(S.ns, psi_prime.words);
+    omega.resize(std::max<size_t>(1, S.ns)); ratio.resize(std::max<size_t>(1, S.ns));
+    d_scal.resize(8);
+    if(S.ns) {
+        ANGPU_CUDA(cudaMemcpyAsync(Sp.conf.p, S.conf.p, sizeof(uint64_t) * S.ns * S.words, cudaMemcpyDeviceToDevice, stream()));
+        ANGPU_CUDA(cudaMemcpyAsync(Sp.weight.p, S.weight.p, sizeof(double) * S.ns, cudaMemcpyDeviceToDevice, stream()));
+        psi_prime.log_psi(Sp, false);
+    }
+    k_hsd_terms<<<1, RED_T, 0, stream()>>>(S.weight.p, S.log_psi.p, Sp.log_psi.p, S.eloc.p, S.ns, is_unitary, omega.p, ratio.p, d_scal.p);
+    ANGPU_CHECK_LAUNCH(); count_launch();
+    allreduce_sum(d_scal.p, 4);
+    if(want_gradient) {
+        g.resize(2 * (size_t)P);
+        rows.evaluated = true;
+        rows.prepare_rows(psi_prime, false);
+        rows.weighted_conj_column_sums(omega.p, g.p);
+        rows.weighted_conj_column_sums(ratio.p, g.p + P);
+        allreduce_sum(reinterpret_cast<double*>(g.p), 4 * (size_t)P);
+    }
+    d_scal.download(h, 4);
+}
+double HilbertSpaceDistance::distance(Psi& psi, Psi& psi_prime, const Operator& op, bool is_unitary, Ensemble& ens) {
+    double h[5]; averages(psi, psi_prime, op, is_unitary, ens, false, h);
+    const double u = h[0] * h[0] + h[1] * h[1], v = h[3] * h[2];
+    return std::sqrt(std::max(1.0 - u / v, 1e-8));
+}
+double HilbertSpaceDistance::gradient(cplx* result, Psi& psi, Psi& psi_prime, const Operator& op, bool is_unitary, Ensemble& ens, float nu) {
+    double h[5]; averages(psi, psi_prime, op, is_unitary, ens, true, h);
+    const cplx om(h[0], h[1]);
+    const double u = abs2(om), v = h[3] * h[2];
+    const double dist = std::sqrt(std::max(1.0 - u / v, 1e-8)), prefactor = std::pow(dist, (double)nu);
+    std::vector<cplx> gh(2 * (size_t)P); g.download(gh.data(), gh.size());
+    for(unsigned k = 0; k < P; k++) {                  // HilbertSpaceDistance.cu.template:160-168
+        const cplx u_k = conj(om) * gh[k];
+        const cplx v_k = h[3] * gh[P + k];
+        const cplx num = u_k * v - u * v_k;
+        result[k] = cplx(-num.re / (v * v) / prefactor, -num.im / (v * v) / prefactor);
+    }
+    return dist;
 }
 
 // ============================================================================================ FP64 peak probe

@@ -90,6 +90,10 @@ struct TDVP {
     // TDVP::eval_F_vector (:306-334).  For PsiRBM the samples are kept in factorised form unless dense rows are requested.
     void eval_F(const Operator& op, Psi& psi, Ensemble& ens) { eval(op, psi, ens, false); }
     double var_H() const { return E2 - abs2(E); }
+    // log-derivative rows of psi at the configurations in S: dense O, or the factorised (conf, T) form for a PsiRBM
+    void prepare_rows(Psi& psi, bool dense);
+    // x_k = sum_s w_s X_s conj(O_sk) over the local samples (deterministic two-stage sum), x_out: [P] device
+    void weighted_conj_column_sums(const cplx* X, cplx* x_out);
     void ensure_dense_O(Psi* psi);
     // out = S v using the samples of the last eval (TDVP::S_dot_vector, :337-443), O(ns*P) instead of the reference's O(ns*P^2)
     void S_dot_vector_dev(const cplx* v_dev, cplx* out_dev);
@@ -109,6 +113,22 @@ struct TDVP {
     float phase_ms[6] = {0, 0, 0, 0, 0, 0};     // sample, eloc, ok+reduce(+allreduce), total, S build, last solve
     void mark(int i);
     ~TDVP();
+};
+
+// HilbertSpaceDistance (include/network_functions/HilbertSpaceDistance.hpp:20-116,
+// source/network_functions/HilbertSpaceDistance.cu.template:16-174): distance between U|psi> (or exp(A)|psi>) and
+// |psi'> estimated on samples of psi, and its gradient with respect to the parameters of psi'.
+struct HilbertSpaceDistance {
+    unsigned P;                      // parameters of psi_prime
+    SampleSet S;                     // samples of psi (conf, log psi, weight, E_loc)
+    TDVP rows;                       // holds psi_prime's rows at the same configurations (rows.S shares conf / weight)
+    DevBuf<cplx> omega, ratio, g;    // per-sample omega_s, probability ratio (as complex), [2P] column sums
+    DevBuf<double> d_scal;
+    explicit HilbertSpaceDistance(unsigned P_) : P(P_), rows(P_) {}
+    double distance(Psi& psi, Psi& psi_prime, const Operator& op, bool is_unitary, Ensemble& ens);
+    double gradient(cplx* result_host, Psi& psi, Psi& psi_prime, const Operator& op, bool is_unitary, Ensemble& ens, float nu);
+private:
+    void averages(Psi& psi, Psi& psi_prime, const Operator& op, bool is_unitary, Ensemble& ens, bool want_gradient, double h[5]);
 };
 
 // free functions (source/network_functions/{PsiVector,PsiNorm,PsiOkVector,ApplyOperator}.cu.template)

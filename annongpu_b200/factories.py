@@ -84,6 +84,24 @@ class PauliSum:
         return Operator(self, gpu)
 
 
+def propagator(H, dt):
+    """First-order time-step operator 1 - i dt H as a PauliSum (identity string a = b = 0): the kind of operator the
+    reference's HilbertSpaceDistance is used with (pyANNonGPU/LearningByGradientDescent.py)."""
+    U = PauliSum(H.num_sites).add(1.0, {})
+    for c, a, b in zip(H.coeffs, H.a, H.b):
+        U.coeffs.append(-1j * dt * c)
+        U.a.append(a)
+        U.b.append(b)
+    return U
+
+
+def scaled(H, factor):
+    """factor * H as a new PauliSum."""
+    out = PauliSum(H.num_sites)
+    out.coeffs, out.a, out.b = [factor * c for c in H.coeffs], list(H.a), list(H.b)
+    return out
+
+
 def ring_bonds(n):
     return [(i, (i + 1) % n) for i in range(n)]
 

@@ -33,6 +33,7 @@ typedef struct angpu_operator_s* angpu_operator_t;   /* Operator = StandartOpera
 typedef struct angpu_ensemble_s* angpu_ensemble_t;   /* MonteCarloSpins | ExactSummationSpins */
 typedef struct angpu_expval_s*   angpu_expval_t;     /* ExpectationValue */
 typedef struct angpu_tdvp_s*     angpu_tdvp_t;       /* TDVP */
+typedef struct angpu_hsd_s*      angpu_hsd_t;        /* HilbertSpaceDistance */
 
 enum { ANGPU_PSI_RBM = 0, ANGPU_PSI_DEEP = 1, ANGPU_PSI_CNN = 2, ANGPU_PSI_CLASSICAL = 3 };
 
@@ -185,6 +186,20 @@ int angpu_tdvp_set_profile(angpu_tdvp_t tdvp, int enable);
 int angpu_tdvp_phase_ms(angpu_tdvp_t tdvp, double out[6]);
 /* measured FP64 FMA throughput of the device (TFLOP/s), the roofline denominator of the FP64-pipe-bound kernels */
 int angpu_measure_fp64_tflops(double* out);
+
+/* ---- HilbertSpaceDistance(num_params, gpu)  (include/network_functions/HilbertSpaceDistance.hpp:55-116,
+ * source/network_functions/HilbertSpaceDistance.cu.template:16-174; pyANNonGPU/main.cpp.template:436-440).
+ * Samples s ~ |psi|^2; with A_loc = local energy of `op` on psi:
+ *   is_unitary: omega_s = exp(conj(log psi'(s) - log psi(s))) A_loc(s),  next-state norm = <|A_loc|^2>
+ *   else:       omega_s = exp(A_loc(s) + conj(log psi'(s) - log psi(s))), next-state norm = <exp(2 Re A_loc)>
+ *   distance = sqrt(max(1 - |<omega>|^2 / (norm <|psi'/psi|^2>), 1e-8));
+ * gradient: d distance / d conj(theta'_k) of psi_prime's parameters divided by distance^nu; returns the distance too. */
+int angpu_hsd_create(unsigned num_params, angpu_hsd_t* out);
+int angpu_hsd_destroy(angpu_hsd_t hsd);
+int angpu_hsd_distance(angpu_hsd_t hsd, angpu_psi_t psi, angpu_psi_t psi_prime, angpu_operator_t op, int is_unitary,
+                       angpu_ensemble_t ens, double* distance_out);
+int angpu_hsd_gradient(angpu_hsd_t hsd, angpu_psi_t psi, angpu_psi_t psi_prime, angpu_operator_t op, int is_unitary,
+                       angpu_ensemble_t ens, float nu, double* gradient_out, double* distance_out);
 
 #ifdef __cplusplus
 }

@@ -411,6 +411,43 @@ def gradient(op, psi, ens):
     return (w * el) @ Oc - E * (w @ Oc), complex(E)
 
 
+def _hsd_averages(psi, psi_prime, op, is_unitary, ens, want_gradient):
+    """kernel::HilbertSpaceDistance::compute_averages (source/network_functions/HilbertSpaceDistance.cu.template:16-89)."""
+    confs, lp, w = _samples_and_weights(psi, ens)
+    _, el, _ = eval_samples(psi, op, confs)
+    lpp, _, Op = eval_samples(psi_prime, None, confs, want_O=want_gradient)
+    if is_unitary:
+        omega = np.exp(np.conj(lpp - lp)) * el
+        next_state_norm = np.sum(w * np.abs(el) ** 2)
+    else:
+        omega = np.exp(el + np.conj(lpp - lp))
+        next_state_norm = np.sum(w * np.exp(2.0 * el.real))
+    pr = np.exp(2.0 * (lpp.real - lp.real))
+    out = {"omega": np.sum(w * omega), "pr": np.sum(w * pr), "nsn": next_state_norm}
+    if want_gradient:
+        out["omega_Ok"] = (w * omega) @ np.conj(Op)
+        out["pr_Ok"] = (w * pr) @ np.conj(Op)
+    return out
+
+
+def hilbert_space_distance(psi, psi_prime, op, is_unitary, ens):
+    """HilbertSpaceDistance::distance (:121-137)."""
+    a = _hsd_averages(psi, psi_prime, op, is_unitary, ens, False)
+    u, v = abs(a["omega"]) ** 2, a["nsn"] * a["pr"]
+    return float(np.sqrt(max(1.0 - u / v, 1e-8)))
+
+
+def hilbert_space_distance_gradient(psi, psi_prime, op, is_unitary, ens, nu):
+    """HilbertSpaceDistance::gradient (:140-171) -> (gradient[P'], distance); nu is a float in the reference."""
+    a = _hsd_averages(psi, psi_prime, op, is_unitary, ens, True)
+    u, v = abs(a["omega"]) ** 2, a["nsn"] * a["pr"]
+    distance = float(np.sqrt(max(1.0 - u / v, 1e-8)))
+    prefactor = distance ** float(np.float32(nu))
+    u_k = np.conj(a["omega"]) * a["omega_Ok"]
+    v_k = a["nsn"] * a["pr_Ok"]
+    return -(u_k * v - u * v_k) / (v * v) / prefactor, distance
+
+
 class TDVP:
     def __init__(self, num_params):
         self.P = int(num_params)

@@ -81,6 +81,8 @@ def lib():
         L.ref_exp_sigma_z.argtypes = [i32, vp, vp, i32, vp, vp]
         L.ref_tdvp_eval_with_psi_ref.argtypes = [vp, i32, vp, vp, i32, vp]
         L.ref_tdvp_eval_with_psi_ref.restype = dbl
+        L.ref_hilbert_space_distance.argtypes = [i32, vp, vp, vp, i32, i32, vp, vp, C.c_float]
+        L.ref_hilbert_space_distance.restype = dbl
         L.ref_set_gpu.argtypes = [i32]
         L.ref_device_synchronize.restype = i32
         _lib = L
@@ -342,6 +344,20 @@ def gradient(op, psi, ens):
     g, e = _cout(psi.num_params), _cout(1)
     lib().ref_gradient(psi.kind, psi.h, op.h, ens.kind, ens.h, _p(g), _p(e))
     return g, complex(e[0])
+
+
+def hilbert_space_distance(psi, psi_prime, op, is_unitary, ens):
+    """HilbertSpaceDistance::distance; (PsiDeep, PsiDeep) or (PsiCNN, PsiCNN) only."""
+    assert psi.kind == psi_prime.kind and psi.kind in (DEEP, CNN)
+    return float(lib().ref_hilbert_space_distance(psi.kind, psi.h, psi_prime.h, op.h, int(bool(is_unitary)), ens.kind, ens.h, None, 0.0))
+
+
+def hilbert_space_distance_gradient(psi, psi_prime, op, is_unitary, ens, nu):
+    """HilbertSpaceDistance::gradient -> (gradient[P'], distance)."""
+    assert psi.kind == psi_prime.kind and psi.kind in (DEEP, CNN)
+    g = _cout(psi_prime.num_params)
+    d = lib().ref_hilbert_space_distance(psi.kind, psi.h, psi_prime.h, op.h, int(bool(is_unitary)), ens.kind, ens.h, _p(g), float(nu))
+    return g, float(d)
 
 
 class TDVP:

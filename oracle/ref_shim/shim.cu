@@ -28,6 +28,7 @@
 #include "network_functions/PsiNorm.hpp"
 #include "network_functions/PsiOkVector.hpp"
 #include "network_functions/ApplyOperator.hpp"
+#include "network_functions/HilbertSpaceDistance.hpp"
 #include "quantum_states.hpp"
 #include "quantum_state/psi_functions.hpp"
 #include "ensembles.hpp"
@@ -335,6 +336,24 @@ void ref_gradient(int kind, void* h, void* op, int ek, void* e, double* grad_out
             copy_out(grad_out, r.first); store(E_out, r.second);
         });
     });
+}
+
+// ---------------------------------------------------------------- HilbertSpaceDistance
+// (include/network_functions/HilbertSpaceDistance.hpp:55-116; instantiated for (PsiDeep, PsiDeep) and (PsiCNN, PsiCNN))
+// grad_out == null: distance only.  Returns the distance.
+double ref_hilbert_space_distance(int kind, void* h, void* h_prime, void* op, int is_unitary, int ek, void* e,
+                                  double* grad_out, float nu) {
+    double d = 0.0;
+    auto run = [&](auto& psi, auto& psi_prime) {
+        HilbertSpaceDistance hsd(psi_prime.num_params, g_gpu);
+        with_ens(ek, e, [&](auto& ens) {
+            if(grad_out) d = hsd.gradient(reinterpret_cast<std::complex<double>*>(grad_out), psi, psi_prime, *static_cast<Operator*>(op), is_unitary != 0, ens, nu);
+            else         d = hsd.distance(psi, psi_prime, *static_cast<Operator*>(op), is_unitary != 0, ens);
+        });
+    };
+    if(kind == DEEP) run(*static_cast<PsiDeep*>(h), *static_cast<PsiDeep*>(h_prime));
+    else if(kind == CNN) run(*static_cast<PsiCNN*>(h), *static_cast<PsiCNN*>(h_prime));
+    return d;
 }
 
 // ---------------------------------------------------------------- TDVP

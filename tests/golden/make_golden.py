@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
-from helpers import classical_zoo, make_classical, make_op, make_psi, zoo   # noqa: E402
+from helpers import classical_zoo, hsd_cases, make_classical, make_op, make_psi, zoo   # noqa: E402
 from oracle import ref_oracle as R                                           # noqa: E402
 
 PROBES = [0x2A5, 0x13, 0x3FF, 0x0]
@@ -62,6 +62,15 @@ def main():
         out[f"{name}/wref/total_weight"] = t.eval_with_psi_ref(make_op(R, H), psi, R.ExactSummation(N))
         out[f"{name}/wref/E"], out[f"{name}/wref/F"], out[f"{name}/wref/Ok"] = t.E_local, t.F_vector, t.O_k_vector
         out[f"{name}/wref/S"] = t.S_matrix
+    # HilbertSpaceDistance (the reference instantiates (PsiDeep, PsiDeep) and (PsiCNN, PsiCNN)); inputs: helpers.hsd_cases()
+    for name, (spec, spec_prime, OP, is_unitary, N) in hsd_cases().items():
+        psi, psi_prime, op, es = make_psi(R, spec), make_psi(R, spec_prime), make_op(R, OP), R.ExactSummation(N)
+        for p in (psi, psi_prime):
+            if hasattr(p, "init_gradient"):
+                p.init_gradient(1 << N)
+        out[f"hsd/{name}/distance"] = R.hilbert_space_distance(psi, psi_prime, op, is_unitary, es)
+        g, d = R.hilbert_space_distance_gradient(psi, psi_prime, op, is_unitary, es, 1.0)
+        out[f"hsd/{name}/gradient"], out[f"hsd/{name}/distance_g"] = g, d
     # primitives: Pauli action (bit-exact) and activation polynomials
     rng = np.random.default_rng(7)
     a, b, c = (rng.integers(0, 1 << 63, size=64, dtype=np.uint64) for _ in range(3))

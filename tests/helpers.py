@@ -93,6 +93,21 @@ def classical_zoo():
     }
 
 
+def hsd_cases():
+    """name -> (spec of psi, spec of psi_prime, operator PauliSum, is_unitary, num_sites) for HilbertSpaceDistance."""
+    z = zoo()
+    deep, Hd, Nd = z["deep2"]
+    deep_p = F.deep_spec(8, 8, [16, 8], [4, 8], noise=2e-2, a=0.05, final_weights=3, seed=22)
+    cnn, Hc, Nc = z["cnn"]
+    cnn_p = F.cnn_spec([2, 2, 3], [(2, [2, 2, 2]), (3, [1, 2, 2])], noise=1.2e-1, final_factor=2, seed=55)
+    return {
+        "deep_unitary": (deep, deep_p, F.propagator(Hd, 0.05), True, Nd),
+        "deep_exp": (deep, deep_p, F.scaled(Hd, -0.05j), False, Nd),
+        "cnn_unitary": (cnn, cnn_p, F.propagator(Hc, 0.02), True, Nc),
+        "cnn_exp": (cnn, cnn_p, F.scaled(Hc, -0.001j), False, Nc),
+    }
+
+
 class GpuAdapter:
     """Presents annongpu_b200 with the oracle modules' function names, so one checker serves both."""
     __name__ = "annongpu_b200"
@@ -121,6 +136,12 @@ class GpuAdapter:
 
     def exp_sigma_z(self, op, psi, ens):
         return self.ev.exp_sigma_z(op, psi, ens)
+
+    def hilbert_space_distance(self, psi, psi_prime, op, is_unitary, ens):
+        return self.A.HilbertSpaceDistance(psi_prime.num_params, True)(psi, psi_prime, op, is_unitary, ens)
+
+    def hilbert_space_distance_gradient(self, psi, psi_prime, op, is_unitary, ens, nu):
+        return self.A.HilbertSpaceDistance(psi_prime.num_params, True).gradient(psi, psi_prime, op, is_unitary, ens, nu)
 
     def TDVP(self, P):
         return self.A.TDVP(P, True)

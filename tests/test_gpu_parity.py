@@ -451,3 +451,33 @@ def test_eval_with_explicit_sampling_state(gpu, port):
     tp.eval_with_psi_ref(op_, pp, port.ExactSummation(N), psi_sampling=sp)
     assert rel_err(tg.S_matrix, tp.S_matrix) <= TOL and rel_err(tg.F_vector, tp.F_vector) <= TOL
     assert abs(tg.total_weight - tp.total_weight) <= TOL * tp.total_weight
+
+
+# ------------------------------------------------------------------------------------------------ SURVEY 8f rank 1
+
+@pytest.mark.parametrize("pair", ["rbm_rbm", "deep_rbm", "rbm_wide"])
+def test_hilbert_space_distance_monte_carlo_and_mixed_models(gpu, port, pair):
+    """HilbertSpaceDistance on Monte-Carlo samples (identical chains) and on model pairs the reference does not
+    instantiate, incl. the factorised PsiRBM rows (M = 600 > the reference's limit) as psi_prime."""
+    if pair == "rbm_rbm":
+        spec, H, N = zoo()["rbm10"]
+        spec_p = F.rbm_spec(10, 20, noise=4e-2, final_weight=9, seed=32)
+    elif pair == "deep_rbm":
+        spec, H, N = zoo()["deep2"]
+        spec_p = F.rbm_spec(8, 16, noise=3e-2, final_weight=2, seed=41)
+    else:
+        spec, H, N = wide_zoo()["rbm_wide"]
+        spec_p = F.rbm_spec(12, 600, noise=2.5e-2, final_weight=0.5, seed=14)
+    U = F.propagator(H, 0.03)
+    pg, qg, og = make_psi(gpu, spec), make_psi(gpu, spec_p), make_op(gpu, U)
+    pp, qp, op_ = make_psi(port, spec), make_psi(port, spec_p), make_op(port, U)
+    hsd = gpu.HilbertSpaceDistance(qg.num_params, True)
+    for eg, ep, tol in ((gpu.ExactSummationSpins(N), port.ExactSummation(N), 1e-9),
+                        (gpu.MonteCarloSpins(384, 1, 4, 48, True, seed=9), port.MonteCarlo(384, 1, 4, 48, seed=9), 1e-8)):
+        d_p = port.hilbert_space_distance(pp, qp, op_, True, ep)
+        assert abs(hsd(pg, qg, og, True, eg) - d_p) <= tol
+        if isinstance(ep, port.MonteCarlo):       # fresh ensembles: the Philox call counter advanced above
+            eg, ep = gpu.MonteCarloSpins(384, 1, 4, 48, True, seed=9), port.MonteCarlo(384, 1, 4, 48, seed=9)
+        g_p, d_p = port.hilbert_space_distance_gradient(pp, qp, op_, True, ep, 0.5)
+        g_g, d_g = hsd.gradient(pg, qg, og, True, eg, 0.5)
+        assert abs(d_g - d_p) <= tol and rel_err(g_g, g_p) <= 1e-7

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from annongpu_b200 import factories as F
-from helpers import classical_zoo, make_classical, make_op, make_psi, rel_err, zoo
+from helpers import classical_zoo, hsd_cases, make_classical, make_op, make_psi, rel_err, zoo
 
 GOLDEN = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_golden.npz"))
 PROBES = [0x2A5, 0x13, 0x3FF, 0x0]
@@ -63,6 +63,21 @@ def test_port_matches_reference_golden_classical(port, name):
     psi = make_classical(port, N, order, Hl, pr, ref_spec, lp)
     check_against_golden(port, name, psi, H, N, port.ExactSummation)
     check_wref_against_golden(port, name, psi, H, N, port.ExactSummation)
+
+
+def check_hsd_against_golden(mod, name, ensemble_cls):
+    spec, spec_prime, OP, is_unitary, N = hsd_cases()[name]
+    psi, psi_prime, op, es = make_psi(mod, spec), make_psi(mod, spec_prime), make_op(mod, OP), ensemble_cls(N)
+    d = mod.hilbert_space_distance(psi, psi_prime, op, is_unitary, es)
+    assert abs(d - GOLDEN[f"hsd/{name}/distance"]) <= 1e-9
+    g, d2 = mod.hilbert_space_distance_gradient(psi, psi_prime, op, is_unitary, es, 1.0)
+    assert abs(d2 - GOLDEN[f"hsd/{name}/distance_g"]) <= 1e-9
+    assert rel_err(g, GOLDEN[f"hsd/{name}/gradient"]) <= 1e-8
+
+
+@pytest.mark.parametrize("name", sorted(hsd_cases()))
+def test_port_hilbert_space_distance_matches_reference_golden(port, name):
+    check_hsd_against_golden(port, name, port.ExactSummation)
 
 
 def test_port_primitives_match_golden(port):
