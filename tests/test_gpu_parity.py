@@ -471,6 +471,10 @@ def test_hilbert_space_distance_monte_carlo_and_mixed_models(gpu, port, pair):
     U = F.propagator(H, 0.03)
     pg, qg, og = make_psi(gpu, spec), make_psi(gpu, spec_p), make_op(gpu, U)
     pp, qp, op_ = make_psi(port, spec), make_psi(port, spec_p), make_op(port, U)
+    # normalise both states (un-normalised exact-summation weights of the wide RBM under/overflow v^2 in the gradient)
+    for a, b in ((pg, pp), (qg, qp)):
+        lp = b.log_prefactor - np.log(port.psi_norm(b, port.ExactSummation(N)))
+        a.log_prefactor = b.log_prefactor = lp
     hsd = gpu.HilbertSpaceDistance(qg.num_params, True)
     for eg, ep, tol in ((gpu.ExactSummationSpins(N), port.ExactSummation(N), 1e-9),
                         (gpu.MonteCarloSpins(384, 1, 4, 48, True, seed=9), port.MonteCarlo(384, 1, 4, 48, seed=9), 1e-8)):
