@@ -1119,8 +1119,11 @@ void TDVP::solve_dense(double shift_abs, double shift_rel, cplx rhs_phase, cplx*
     const size_t n = P;
     DevBuf<double> dg;
     if(shift_rel != 0.0) tdvp_diag(*this, dg); else { dg.resize(n); dg.zero(); }
-    // row-major Hermitian S read as column-major is conj(S): solve conj(S) y = conj(b), x = conj(y)
-    DevBuf<cplx> A(n * n), b(n);
+    // row-major Hermitian S read as column-major is conj(S): solve conj(S) y = conj(b), x = conj(y).
+    // The factorisation workspace (a copy of S, 16 P^2 bytes) is a grow-only member: cudaMalloc/cudaFree of a GB-sized
+    // buffer per call cost 0.1-0.8 s on some boxes.
+    DevBuf<cplx>& A = solve_A; DevBuf<cplx>& b = solve_b; DevBuf<cplx>& work = solve_work; DevBuf<int>& info = solve_info;
+    b.resize(n);
     A.copy_from(Smat);
     k_add_diag_shift<<<grid_for(n), 256, 0, stream()>>>(A.p, dg.p, shift_abs, shift_rel, P);
     k_scale_vec<<<grid_for(n), 256, 0, stream()>>>(F.p, rhs_phase, b.p, n, false);
@@ -1134,7 +1137,7 @@ void TDVP::solve_dense(double shift_abs, double shift_rel, cplx rhs_phase, cplx*
     // handle and workspace exist (the first call costs 100-500 ms); a hand-blocked ZHERK/ZTRSM variant was slower (36 ms).
     int lwork = 0;
     if(cusolverDnZpotrf_bufferSize(g_cusolver, CUBLAS_FILL_MODE_LOWER, ni, Ad, ni, &lwork) != CUSOLVER_STATUS_SUCCESS) throw Error("Zpotrf_bufferSize failed");
-    DevBuf<cplx> work((size_t)std::max(lwork, 1)); DevBuf<int> info(2);
+    work.resize((size_t)std::max(lwork, 1)); info.resize(2);
     const int nblk = 1;
     if(cusolverDnZpotrf(g_cusolver, CUBLAS_FILL_MODE_LOWER, ni, Ad, ni, reinterpret_cast<cuDoubleComplex*>(work.p), lwork, info.p) != CUSOLVER_STATUS_SUCCESS) throw Error("Zpotrf failed");
     int hinfo = 0; info.download(&hinfo, 1);

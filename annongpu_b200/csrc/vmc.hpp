@@ -106,6 +106,8 @@ struct TDVP {
     // opt-in fast path: 3xTF32 on tcgen05 tensor cores (sbuild_tc.cu), ~1e-5 relative to ||S||
     void build_S_tensorcore();
     DevBuf<float> tc_planes;
+    DevBuf<cplx> solve_A, solve_b, solve_work;   // dense-solve workspace (grow-only)
+    DevBuf<int> solve_info;
     Psi* last_psi = nullptr;
     // optional phase timing (bench.py): CUDA events on the library stream around sample / E_loc / O_k+reduce
     bool profile = false;
