@@ -129,27 +129,44 @@ void PsiRBM::ensure_angles(SampleSet& S) {
     ANGPU_CHECK_LAUNCH(); count_launch();
     S.has_angles = true;
 }
+template<int WPS>
+static void launch_eloc_rbm(const RbmDev& d, const Operator& op, SampleSet& S) {
+    constexpr unsigned TEAMS = RBM_ELOC_WARPS / WPS;
+    const size_t smem = TEAMS * rbm_eloc_slice_bytes(d.M, op.dev.num_groups, WPS);
+    const unsigned grid = (unsigned)std::min<size_t>((S.ns + TEAMS - 1) / TEAMS, (size_t)ctx().num_sms * 32);
+    auto launch = [&](auto kernel) {
+        set_smem(kernel, smem);
+        kernel<<<grid, RBM_ELOC_WARPS * 32, smem, stream()>>>(d, op.dev, S.conf.p, S.angles.p, S.ns, S.eloc.p);
+    };
+    switch(op.dev.max_flips) {
+        case 0: case 1: launch(k_eloc_rbm<1, WPS>); break;
+        case 2: launch(k_eloc_rbm<2, WPS>); break;
+        case 3: launch(k_eloc_rbm<3, WPS>); break;
+        default: launch(k_eloc_rbm<4, WPS>); break;
+    }
+    ANGPU_CHECK_LAUNCH(); count_launch();
+}
 void PsiRBM::eloc(const Operator& op, SampleSet& S) {
     if(S.ns == 0) return;
     ANGPU_REQUIRE(op.words == words, "operator / wavefunction word count mismatch");
-    const size_t slice = rbm_eloc_slice_bytes(M, op.dev.num_groups);
     const size_t budget = std::min<size_t>(ctx().smem_optin, 200 * 1024);
-    if(op.dev.max_flips > (unsigned)RBM_ELOC_MAXF || slice > budget) { generic_eloc(dev(), op, S); return; }
+    if(op.dev.max_flips > (unsigned)RBM_ELOC_MAXF || rbm_eloc_slice_bytes(M, op.dev.num_groups, RBM_ELOC_WARPS) > budget) { generic_eloc(dev(), op, S); return; }
     ensure_angles(S);
-    unsigned wpb = (unsigned)std::min<size_t>(8, budget / slice);
-    while(wpb > 1 && wpb * slice > budget / 2) wpb--;
-    const unsigned grid = (unsigned)std::min<size_t>((S.ns + wpb - 1) / wpb, (size_t)ctx().num_sms * 16);
-    auto launch = [&](auto kernel) {
-        set_smem(kernel, wpb * slice);
-        kernel<<<grid, wpb * 32, wpb * slice, stream()>>>(dev(), op.dev, S.conf.p, S.angles.p, S.ns, S.eloc.p);
-    };
-    switch(op.dev.max_flips) {
-        case 0: case 1: launch(k_eloc_rbm<1>); break;
-        case 2: launch(k_eloc_rbm<2>); break;
-        case 3: launch(k_eloc_rbm<3>); break;
-        default: launch(k_eloc_rbm<4>); break;
+    // warps per sample: as few as keep >= 4 blocks (32 warps) per SM resident, but at least 2 (finer scheduling units);
+    // ANGPU_ELOC_WPS overrides (A/B timing)
+    const char* env = getenv("ANGPU_ELOC_WPS");
+    unsigned wps = env ? (unsigned)atoi(env) : 0u;
+    if(wps != 1u && wps != 2u && wps != 4u && wps != 8u) {
+        wps = 2u;
+        while(wps < (unsigned)RBM_ELOC_WARPS && (RBM_ELOC_WARPS / wps) * rbm_eloc_slice_bytes(M, op.dev.num_groups, wps) > (size_t)ctx().smem_optin / 4) wps *= 2u;
     }
-    ANGPU_CHECK_LAUNCH(); count_launch();
+    const RbmDev d = dev();
+    switch(wps) {
+        case 1: launch_eloc_rbm<1>(d, op, S); break;
+        case 2: launch_eloc_rbm<2>(d, op, S); break;
+        case 4: launch_eloc_rbm<4>(d, op, S); break;
+        default: launch_eloc_rbm<8>(d, op, S); break;
+    }
 }
 void PsiRBM::compute_T(SampleSet& S, DevBuf<cplx>& T) {
     ensure_angles(S);
@@ -422,17 +439,19 @@ void PsiCNN::build() {
     ANGPU_REQUIRE(off == P, "PsiCNN: parameter count does not match the layer description");
     d_sym.upload(sym); d_params.upload(params);
 }
-CnnDev PsiCNN::dev() const {
+CnnDev PsiCNN::dev(bool keep_angles) const {
     CnnDev d{};
+    d.keep_angles = keep_angles;
     d.N = N; d.words = words; d.P = P; d.num_layers = num_layers; d.num_sym = num_sym; d.num_angles = num_angles; d.maxch = maxch;
     d.final_factor = final_factor; d.lp = lp; d.sym = d_sym.p; d.params = d_params.p;
     for(unsigned l = 0; l < num_layers; l++) d.L[l] = layer_dev[l];
     return d;
 }
-void PsiCNN::log_psi(SampleSet& S, bool es_weights) { generic_log_psi(dev(), S, es_weights); }
-void PsiCNN::eloc(const Operator& op, SampleSet& S) { generic_eloc(dev(), op, S); }
-void PsiCNN::ok_rows(SampleSet& S, size_t s0, size_t cnt, cplx* out) { generic_ok(dev(), S, s0, cnt, out); }
-void PsiCNN::mc_sample(const McParams& mc, SampleSet& S, unsigned long long* a) { generic_mc(dev(), mc, S, a); }
+// only O_k (back-propagation) needs the recorded pre-activations: the other kernels run with the smaller per-warp scratch
+void PsiCNN::log_psi(SampleSet& S, bool es_weights) { generic_log_psi(dev(false), S, es_weights); }
+void PsiCNN::eloc(const Operator& op, SampleSet& S) { generic_eloc(dev(false), op, S); }
+void PsiCNN::ok_rows(SampleSet& S, size_t s0, size_t cnt, cplx* out) { generic_ok(dev(true), S, s0, cnt, out); }
+void PsiCNN::mc_sample(const McParams& mc, SampleSet& S, unsigned long long* a) { generic_mc(dev(false), mc, S, a); }
 
 // ---------------------------------------------------------------------------------------- PsiClassical
 

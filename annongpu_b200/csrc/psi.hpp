@@ -117,7 +117,7 @@ struct PsiCNN : Psi {
     PsiCNN(const unsigned* extent_, unsigned num_layers_, const unsigned* num_channels_, const unsigned* connectivity_,
            const unsigned* symmetry_classes, const cplx* params_, unsigned num_params, double final_factor_, cplx lp_);
     void build();
-    CnnDev dev() const;
+    CnnDev dev(bool keep_angles = true) const;
     Psi* clone() const override {
         return new PsiCNN(extent, num_layers, num_channels.data(), connectivity.data(), sym.data(), params.data(), P, final_factor, lp);
     }

@@ -209,14 +209,16 @@ struct CnnLayerDev {
 };
 struct CnnDev {
     unsigned N, words, P, num_layers, num_sym, num_angles, maxch;
+    bool     keep_angles;      // pre-activations are recorded only for O_k (back-propagation); samplers / E_loc drop them
     double   final_factor;
     cplx     lp;
     const unsigned* sym;       // [N]
     const cplx*     params;    // [P]
     CnnLayerDev     L[CNN_MAX_LAYERS];
 
-    // scratch: in[maxch*N] | out[maxch*N] | angles[num_angles]
-    __host__ __device__ unsigned payload_elems() const { return 2u * maxch * N + num_angles; }
+    // scratch: in[maxch*N] | out[maxch*N] | angles[num_angles] (the last only when keep_angles: 14.4 of 24 KB per warp
+    // at C3, i.e. 2.5x the resident warps for the sampler and E_loc without it)
+    __host__ __device__ unsigned payload_elems() const { return 2u * maxch * N + (keep_angles ? num_angles : 0u); }
     // the weights are staged once per block in shared memory (broadcast LDS instead of L1 round trips) when they fit
     __host__ __device__ unsigned block_scratch_bytes() const { return (P <= 1024u) ? P * (unsigned)sizeof(cplx) : 0u; }
 #ifdef __CUDACC__
@@ -272,18 +274,18 @@ struct CnnDev {
             }
             #pragma unroll
             for(int cj = 0; cj < NCH; cj++) {
-                angles[ly.angle_off + (unsigned)cj * N + x] = acc[cj];
+                if(angles) angles[ly.angle_off + (unsigned)cj * N + x] = acc[cj];
                 out[(unsigned)cj * N + x] = act_lc(acc[cj], l);
             }
         }
     }
-    // forward_pass, PsiCNN.hpp:99-160 (angles always recorded into the warp's scratch).  One lane per lattice site x: the
+    // forward_pass, PsiCNN.hpp:99-160 (angles recorded into the warp's scratch when keep_angles).  One lane per lattice site x: the
     // vol neighbour indices are loaded once, every input value is read once from shared memory and used for ALL output
     // channels (register accumulators), so the inner loop is FP64-bound instead of load-bound.
     __device__ cplx forward(const uint64_t* conf, cplx* pl, const unsigned char* blk) const {
         const unsigned lane = threadIdx.x & 31u;
         const cplx* __restrict__ wgt = blk ? reinterpret_cast<const cplx*>(blk) : params;
-        cplx* in = pl; cplx* out = pl + maxch * N; cplx* angles = out + maxch * N;
+        cplx* in = pl; cplx* out = pl + maxch * N; cplx* angles = keep_angles ? out + maxch * N : nullptr;
         for(unsigned j = lane; j < N; j += 32u) in[j] = cplx(spin_at(conf, j), 0.0);
         __syncwarp();
         cplx result(0.0, 0.0);

@@ -371,56 +371,89 @@ __global__ void k_rbm_angles(const RbmDev psi, const uint64_t* __restrict__ conf
 
 constexpr int RBM_ELOC_MAXF = 4;   // flips per group handled by the fast path (Heisenberg/TFIM: <= 2)
 constexpr int RBM_ELOC_SPLIT = 4;  // lanes per flip group: each takes the hidden units j = p (mod 4)
+constexpr int RBM_ELOC_WARPS = 8;  // warps per block
 
-// smem per warp: theta[M] cplx | list_C[num_groups] cplx | list_g[num_groups] unsigned (padded to 16 B)
-__host__ __device__ inline size_t rbm_eloc_slice_bytes(unsigned M, unsigned num_groups) {
-    return (size_t)M * sizeof(cplx) + (size_t)num_groups * sizeof(cplx) + (((size_t)num_groups * sizeof(unsigned) + 15u) & ~(size_t)15u);
+// smem per TEAM (= the WPS warps sharing one sample): theta[M] cplx | list_C[num_groups] cplx | red[2*WPS] cplx |
+// list_g[num_groups] unsigned | count (padded to 16 B)
+__host__ __device__ inline size_t rbm_eloc_slice_bytes(unsigned M, unsigned num_groups, unsigned wps = 1u) {
+    return (size_t)(M + num_groups + 2u * wps) * sizeof(cplx) + ((((size_t)num_groups + 1u) * sizeof(unsigned) + 15u) & ~(size_t)15u);
 }
 
-// One warp per sample.  Work item = (active flip group, quarter of the hidden units); 32 items per pass, so a sample
-// with `a` active groups needs ceil(a/8) passes of M/4 units each (a = #antiparallel bonds ~ N/2 for the Heisenberg ring).
-// theta_j is read from shared memory (4 consecutive complex per quad: conflict-free), W^T[j][site] from L1/L2
-// (8 consecutive sites x 4 rows per instruction); NF = max flips per group (compile time, unused slots have delta = 0).
-template<int NF>
-__global__ void __launch_bounds__(256)
+// barrier over the WPS warps of a team (a whole block when WPS == RBM_ELOC_WARPS): named barrier 1 + team id
+template<int WPS>
+__device__ __forceinline__ void team_sync(unsigned team) {
+    if(WPS == 1) __syncwarp();
+    else if(WPS == RBM_ELOC_WARPS) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" :: "r"(team + 1u), "r"(WPS * 32) : "memory");
+}
+
+// E_loc for PsiRBM: a TEAM of WPS warps per sample.  Work item = (active flip group, quarter of the hidden units): 8 items
+// per warp and pass, so a sample with `a` active groups needs ceil(a / (8 WPS)) passes of M/4 units each (a = number of
+// antiparallel bonds ~ N/2 for the Heisenberg ring).  theta_j is shared by the team in shared memory (4 consecutive
+// complex per quad: conflict-free, broadcast across the 8 groups of a warp); W[site][j] from L1/L2 (4 consecutive
+// hidden units = 64 contiguous bytes per quad and site).  NF = max flips per group (compile time; unused slots have
+// delta = 0).  WPS > 1 keeps the per-sample scratch (16 M bytes) at one copy per team -- for M = 1600 a warp-private copy
+// limits an SM to 5 resident warps -- and makes the work per scheduling unit finer (less tail at ns / SMs ~ 55).
+template<int NF, int WPS>
+__global__ void __launch_bounds__(RBM_ELOC_WARPS * 32)
 k_eloc_rbm(const RbmDev psi, const OpDev op, const uint64_t* __restrict__ confs, const cplx* __restrict__ angles,
            size_t ns, cplx* __restrict__ eloc_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const unsigned lane = threadIdx.x & 31u, wpb = blockDim.x >> 5;
-    const unsigned M = psi.M, N = psi.N, G = op.num_groups;
-    unsigned char* base = smem_raw + (size_t)(threadIdx.x >> 5) * rbm_eloc_slice_bytes(M, G);
+    constexpr unsigned TEAMS = RBM_ELOC_WARPS / WPS, TT = WPS * 32u;      // teams per block, threads per team
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned team = warp / WPS, wid = warp % WPS, ttid = wid * 32u + lane;
+    const unsigned M = psi.M, G = op.num_groups;
+    unsigned char* base = smem_raw + (size_t)team * rbm_eloc_slice_bytes(M, G, WPS);
     cplx* theta = reinterpret_cast<cplx*>(base);
     cplx* list_C = theta + M;
-    unsigned* list_g = reinterpret_cast<unsigned*>(list_C + G);
-    const cplx* __restrict__ Wt = psi.Wt;
-    const unsigned part = lane & (RBM_ELOC_SPLIT - 1), slot = lane / RBM_ELOC_SPLIT;   // 8 groups per pass
+    cplx* red = list_C + G;                                               // [2][WPS]
+    unsigned* list_g = reinterpret_cast<unsigned*>(red + 2 * WPS);
+    unsigned* count_sh = list_g + G;
+    const cplx* __restrict__ W = psi.W;
+    const unsigned part = lane & (RBM_ELOC_SPLIT - 1), slot = wid * (32u / RBM_ELOC_SPLIT) + lane / RBM_ELOC_SPLIT;
 
-    for(size_t s = (size_t)blockIdx.x * wpb + (threadIdx.x >> 5); s < ns; s += (size_t)gridDim.x * wpb) {
+    // team-wide sum of one complex per thread, identical on all threads of the team
+    auto team_sum = [&](cplx v, unsigned which) -> cplx {
+        v = warp_sum(v);
+        if(WPS == 1) return v;
+        if(lane == 0) red[which * WPS + wid] = v;
+        team_sync<WPS>(team);
+        cplx t(0.0, 0.0);
+        #pragma unroll
+        for(int q = 0; q < WPS; q++) t += red[which * WPS + q];
+        return t;
+    };
+
+    for(size_t s = (size_t)blockIdx.x * TEAMS + team; s < ns; s += (size_t)gridDim.x * TEAMS) {
         uint64_t conf[MAXW];
         conf_load(conf, confs + s * psi.words, psi.words);
         cplx basep(0.0, 0.0);
-        for(unsigned j = lane; j < M; j += 32u) { const cplx a = angles[s * M + j]; theta[j] = a; basep += lc0_pq(a.re, a.im); }
-        const cplx base_sum = warp_sum(basep);
+        for(unsigned j = ttid; j < M; j += TT) { const cplx a = angles[s * M + j]; theta[j] = a; basep += lc0_pq(a.re, a.im); }
 
-        // diagonal strings + per-group coefficients, compacted
+        // diagonal strings (spread over the team) + per-group coefficients, compacted by the team's first warp
         cplx E(0.0, 0.0);
-        for(unsigned n = lane; n < op.num_diag; n += 32u) E += string_sign_reg(op, n, conf) * op.coef[n];
-        unsigned count = 0;
-        for(unsigned g0 = 0; g0 < G; g0 += 32u) {
-            const unsigned g = g0 + lane;
-            cplx C(0.0, 0.0);
-            if(g < G) C = strings_coefficient_reg(op, op.group_begin[g], op.group_begin[g + 1u], conf);
-            const bool active = (C.re != 0.0 || C.im != 0.0);
-            const unsigned ballot = __ballot_sync(FULL, active);
-            if(active) {
-                const unsigned pos = count + __popc(ballot & ((1u << lane) - 1u));
-                list_C[pos] = C; list_g[pos] = g;
+        for(unsigned n = ttid; n < op.num_diag; n += TT) E += string_sign_reg(op, n, conf) * op.coef[n];
+        if(wid == 0) {
+            unsigned count = 0;
+            for(unsigned g0 = 0; g0 < G; g0 += 32u) {
+                const unsigned g = g0 + lane;
+                cplx C(0.0, 0.0);
+                if(g < G) C = strings_coefficient_reg(op, op.group_begin[g], op.group_begin[g + 1u], conf);
+                const bool active = (C.re != 0.0 || C.im != 0.0);
+                const unsigned ballot = __ballot_sync(FULL, active);
+                if(active) {
+                    const unsigned pos = count + __popc(ballot & ((1u << lane) - 1u));
+                    list_C[pos] = C; list_g[pos] = g;
+                }
+                count += __popc(ballot);
             }
-            count += __popc(ballot);
+            if(lane == 0) *count_sh = count;
         }
-        __syncwarp();
+        const cplx base_sum = team_sum(basep, 0u);       // (WPS > 1: its barrier also publishes theta, the lists and count)
+        if(WPS == 1) __syncwarp();
+        const unsigned count = *count_sh;
 
-        for(unsigned idx0 = 0; idx0 < count; idx0 += 32u / RBM_ELOC_SPLIT) {
+        for(unsigned idx0 = 0; idx0 < count; idx0 += TT / RBM_ELOC_SPLIT) {
             const unsigned idx = idx0 + slot;
             const bool valid = idx < count;
             unsigned site[NF]; double dl[NF];
@@ -440,13 +473,15 @@ k_eloc_rbm(const RbmDev psi, const OpDev op, const uint64_t* __restrict__ confs,
                     }
                 }
             }
+            const cplx* __restrict__ wr[NF];
+            #pragma unroll
+            for(int f = 0; f < NF; f++) wr[f] = W + (size_t)site[f] * M;
             cplx acc(0.0, 0.0);
             #pragma unroll 4
             for(unsigned j = part; j < M; j += RBM_ELOC_SPLIT) {
                 cplx a = theta[j];
-                const cplx* __restrict__ wr = Wt + (size_t)j * N;
                 #pragma unroll
-                for(int f = 0; f < NF; f++) { const cplx w = ldg(&wr[site[f]]); a.re = fma(dl[f], w.re, a.re); a.im = fma(dl[f], w.im, a.im); }
+                for(int f = 0; f < NF; f++) { const cplx w = ldg(&wr[f][j]); a.re = fma(dl[f], w.re, a.re); a.im = fma(dl[f], w.im, a.im); }
                 acc += lc0_pq(a.re, a.im);
             }
             // combine the 4 quarters of each group
@@ -457,9 +492,9 @@ k_eloc_rbm(const RbmDev psi, const OpDev op, const uint64_t* __restrict__ confs,
             }
             if(valid && part == 0) E += list_C[idx] * cexp(psi.fw * (acc - base_sum));
         }
-        E = warp_sum(E);
-        if(lane == 0) eloc_out[s] = E;
-        __syncwarp();
+        E = team_sum(E, 1u);
+        if(ttid == 0) eloc_out[s] = E;
+        team_sync<WPS>(team);                             // the scratch is reused by the next sample
     }
 }
 
