@@ -2,6 +2,7 @@
 #include "psi.hpp"
 #include "rbm_kernels.cuh"
 #include "deep_kernels.cuh"
+#include "cnn_kernels.cuh"
 #include <algorithm>
 #include <set>
 #include <string>
@@ -438,6 +439,26 @@ void PsiCNN::build() {
     }
     ANGPU_REQUIRE(off == P, "PsiCNN: parameter count does not match the layer description");
     d_sym.upload(sym); d_params.upload(params);
+    // receptive cones for the incremental sampler: affected_0(p) = {x : p in nbr_0(x, .)}, affected_l = preimage of affected_{l-1}
+    d_aff.clear(); d_aff_cnt.clear(); d_aff.resize(num_layers); d_aff_cnt.resize(num_layers);
+    std::vector<std::vector<std::vector<unsigned>>> cone(num_layers, std::vector<std::vector<unsigned>>(N));
+    for(unsigned l = 0; l < num_layers; l++) {
+        const unsigned vol = layer_dev[l].vol;
+        aff_max[l] = 0;
+        for(unsigned p = 0; p < N; p++) {
+            std::set<unsigned> out;
+            if(l == 0) for(unsigned c = 0; c < vol; c++) out.insert(h_inv[0][(size_t)p * vol + c]);
+            else for(unsigned y : cone[l - 1][p]) for(unsigned c = 0; c < vol; c++) out.insert(h_inv[l][(size_t)y * vol + c]);
+            cone[l][p].assign(out.begin(), out.end());
+            aff_max[l] = std::max<unsigned>(aff_max[l], (unsigned)out.size());
+        }
+        std::vector<unsigned> flat((size_t)N * aff_max[l], 0u), cnt(N);
+        for(unsigned p = 0; p < N; p++) {
+            cnt[p] = (unsigned)cone[l][p].size();
+            std::copy(cone[l][p].begin(), cone[l][p].end(), flat.begin() + (size_t)p * aff_max[l]);
+        }
+        d_aff[l].upload(flat); d_aff_cnt[l].upload(cnt);
+    }
 }
 CnnDev PsiCNN::dev(bool keep_angles) const {
     CnnDev d{};
@@ -451,7 +472,31 @@ CnnDev PsiCNN::dev(bool keep_angles) const {
 void PsiCNN::log_psi(SampleSet& S, bool es_weights) { generic_log_psi(dev(false), S, es_weights); }
 void PsiCNN::eloc(const Operator& op, SampleSet& S) { generic_eloc(dev(false), op, S); }
 void PsiCNN::ok_rows(SampleSet& S, size_t s0, size_t cnt, cplx* out) { generic_ok(dev(true), S, s0, cnt, out); }
-void PsiCNN::mc_sample(const McParams& mc, SampleSet& S, unsigned long long* a) { generic_mc(dev(false), mc, S, a); }
+void PsiCNN::mc_sample(const McParams& mc, SampleSet& S, unsigned long long* a) {
+    const CnnDev d = dev(false);
+    CnnIncDev inc{};
+    inc.backup_elems = 0;
+    for(unsigned l = 0; l < num_layers; l++) {
+        inc.aff[l] = d_aff[l].p; inc.aff_cnt[l] = d_aff_cnt[l].p; inc.aff_max[l] = aff_max[l];
+        inc.backup_elems += layer_dev[l].nch * aff_max[l];
+    }
+    const size_t slice = cnn_inc_slice_bytes(d, inc), bb = d.block_scratch_bytes();
+    const size_t cap = ctx().smem_optin;
+    const char* env = getenv("ANGPU_CNN_SAMPLER");             // "generic" forces the full-forward kernel (tests, A/B timing)
+    if((env && std::string(env) == "generic") || bb == 0 || slice + bb > cap) { generic_mc(d, mc, S, a); return; }
+    if(mc.num_chains_local == 0) return;
+    // warps per block: the choice that keeps the most warps resident per SM (shared memory is the limit)
+    unsigned wpb = 1, best = 0;
+    for(unsigned w = 1; w <= 4; w++) {
+        if(w * slice + bb > cap) break;
+        const unsigned resident = w * (unsigned)std::min<size_t>(32, (size_t)(228 * 1024) / (w * slice + bb + 1024));
+        if(resident >= best) { best = resident; wpb = w; }
+    }
+    const size_t smem = wpb * slice + bb;
+    set_smem(k_mc_cnn_inc, smem);
+    k_mc_cnn_inc<<<ceil_div(mc.num_chains_local, wpb), wpb * 32, smem, stream()>>>(d, inc, mc, S.conf.p, S.log_psi.p, a);
+    ANGPU_CHECK_LAUNCH(); count_launch();
+}
 
 // ---------------------------------------------------------------------------------------- PsiClassical
 

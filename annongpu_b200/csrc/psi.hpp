@@ -113,6 +113,9 @@ struct PsiCNN : Psi {
     DevBuf<unsigned> d_sym; DevBuf<cplx> d_params;
     std::vector<DevBuf<unsigned>> d_nbr, d_inv;
     CnnLayerDev layer_dev[CNN_MAX_LAYERS];
+    // incremental sampler (cnn_kernels.cuh): per layer and flipped site, the output sites inside the receptive cone
+    std::vector<DevBuf<unsigned>> d_aff, d_aff_cnt;
+    unsigned aff_max[CNN_MAX_LAYERS] = {0, 0, 0, 0};
 
     PsiCNN(const unsigned* extent_, unsigned num_layers_, const unsigned* num_channels_, const unsigned* connectivity_,
            const unsigned* symmetry_classes, const cplx* params_, unsigned num_params, double final_factor_, cplx lp_);

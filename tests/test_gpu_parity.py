@@ -485,3 +485,23 @@ def test_hilbert_space_distance_monte_carlo_and_mixed_models(gpu, port, pair):
         g_p, d_p = port.hilbert_space_distance_gradient(pp, qp, op_, True, ep, 0.5)
         g_g, d_g = hsd.gradient(pg, qg, og, True, eg, 0.5)
         assert abs(d_g - d_p) <= tol and rel_err(g_g, g_p) <= 1e-7
+
+
+@pytest.mark.parametrize("name", ["cnn", "cnn_sym", "C3"])
+def test_cnn_incremental_sampler_bit_identical_to_full_forward(gpu, name):
+    """The incremental PsiCNN sampler (cnn_kernels.cuh: only the receptive cone of the flipped site is recomputed) must
+    reproduce the full-forward kernel exactly: same configurations, same acceptances, log psi equal bit for bit."""
+    import os
+    spec = F.config_C3()[0] if name == "C3" else zoo()[name][0]
+    psi = make_psi(gpu, spec)
+    out = {}
+    try:
+        for mode in ("incremental", "generic"):
+            os.environ["ANGPU_CNN_SAMPLER"] = mode
+            mc = gpu.MonteCarloSpins(37 * 3, 2, 3, 37, True, seed=17)
+            out[mode] = mc.sample(psi) + (mc.acceptances,)
+    finally:
+        os.environ["ANGPU_CNN_SAMPLER"] = "incremental"
+    assert np.array_equal(out["incremental"][0], out["generic"][0])
+    assert np.array_equal(out["incremental"][1], out["generic"][1])
+    assert out["incremental"][2] == out["generic"][2]
