@@ -541,38 +541,6 @@ __global__ void k_sv_finish(const cplx* part, unsigned chunks, const cplx* __res
         out[k] = a;
     }
 }
-// One CG iteration's vector work in ONE single-block kernel (n <= 64k): pAp -> alpha -> x, r -> |r|^2 -> beta -> p,
-// and the dot product Obar . p_new needed by the next S.v.   scal: [0] rs, [1] pAp, [2] rs_new, [3] Obar.p
-__global__ void __launch_bounds__(RED_T) k_cg_fused(cplx* __restrict__ x, cplx* __restrict__ r, cplx* __restrict__ p, const cplx* __restrict__ Ap,
-                                                    const cplx* __restrict__ Obar, cplx* __restrict__ scal, size_t n) {
-    __shared__ double bc[2];
-    double v[2] = {0, 0}, red[2];
-    for(size_t k = threadIdx.x; k < n; k += RED_T) { const cplx a = conj(p[k]) * Ap[k]; v[0] += a.re; v[1] += a.im; }
-    block_reduce<2>(v, red);
-    if(threadIdx.x == 0) { bc[0] = scal[0].re / red[0]; scal[1] = cplx(red[0], red[1]); }
-    __syncthreads();
-    const double alpha = bc[0];
-    v[0] = 0.0; v[1] = 0.0;
-    for(size_t k = threadIdx.x; k < n; k += RED_T) {
-        x[k] += alpha * p[k];
-        const cplx rk = r[k] - alpha * Ap[k];
-        r[k] = rk;
-        v[0] += abs2(rk);
-    }
-    block_reduce<2>(v, red);
-    if(threadIdx.x == 0) { bc[1] = red[0] / scal[0].re; scal[2] = cplx(red[0], 0.0); }
-    __syncthreads();
-    const double beta = bc[1];
-    v[0] = 0.0; v[1] = 0.0;
-    for(size_t k = threadIdx.x; k < n; k += RED_T) {
-        const cplx pk = r[k] + beta * p[k];
-        p[k] = pk;
-        const cplx d = Obar[k] * pk;
-        v[0] += d.re; v[1] += d.im;
-    }
-    block_reduce<2>(v, red);
-    if(threadIdx.x == 0) { scal[0] = scal[2]; scal[3] = cplx(red[0], red[1]); }
-}
 
 // ============================================================================================ multi-block CG vector kernels
 // (n > 64k, e.g. C5 with P = 320000): per-block partial sums in a fixed number of blocks, summed by every consumer in
@@ -615,27 +583,54 @@ __global__ void __launch_bounds__(VB_T) k_dot_part(const cplx* __restrict__ a, c
     if(threadIdx.x == 0) part[blockIdx.x] = cplx(r[0], r[1]);
 }
 __global__ void k_sum_part_to_scalar(const cplx* __restrict__ part, cplx* out) { if(threadIdx.x == 0) *out = sum_partials(part); }
-// alpha = rs / sum(part_pAp); x += alpha p; r -= alpha Ap; part_rr[b] = sum |r|^2
+// (Preconditioned) CG vector updates.  scal[0] = (r.z, |r|^2) of the current residual, z = minv * r (Jacobi) or z = r
+// (minv == null); scal[2] receives the same pair for the updated residual and is rolled into scal[0] by k_dot_part.
+// alpha = r.z / sum(part_pAp); x += alpha p; r -= alpha Ap; part_rr[b] = (sum minv |r|^2, sum |r|^2)
 __global__ void __launch_bounds__(VB_T) k_cg_xr_mb(cplx* __restrict__ x, cplx* __restrict__ r, const cplx* __restrict__ p, const cplx* __restrict__ Ap,
-                                                   const cplx* __restrict__ scal, const cplx* __restrict__ part_pAp, cplx* __restrict__ part_rr, size_t n) {
+                                                   const cplx* __restrict__ scal, const cplx* __restrict__ part_pAp, cplx* __restrict__ part_rr,
+                                                   const double* __restrict__ minv, size_t n) {
     const double alpha = scal[0].re / sum_partials(part_pAp).re;
-    double v[1] = {0}, red[1];
+    double v[2] = {0, 0}, red[2];
     for(size_t k = (size_t)blockIdx.x * VB_T + threadIdx.x; k < n; k += (size_t)VB_BLOCKS * VB_T) {
         x[k] += alpha * p[k];
         const cplx rk = r[k] - alpha * Ap[k];
         r[k] = rk;
-        v[0] += abs2(rk);
+        const double a2 = abs2(rk);
+        v[1] += a2;
+        v[0] += minv ? minv[k] * a2 : a2;
     }
-    block_reduce_small<1>(v, red);
-    if(threadIdx.x == 0) part_rr[blockIdx.x] = cplx(red[0], 0.0);
+    block_reduce_small<2>(v, red);
+    if(threadIdx.x == 0) part_rr[blockIdx.x] = cplx(red[0], red[1]);
 }
-// rs_new = sum(part_rr); beta = rs_new / rs; p = r + beta p; scal[2] = rs_new
+// (rz_new, rr_new) = sum(part_rr); beta = rz_new / rz; p = z + beta p; scal[2] = (rz_new, rr_new)
 __global__ void __launch_bounds__(VB_T) k_cg_p_mb(cplx* __restrict__ p, const cplx* __restrict__ r, cplx* __restrict__ scal,
-                                                  const cplx* __restrict__ part_rr, size_t n) {
-    const double rs_new = sum_partials(part_rr).re;
-    const double beta = rs_new / scal[0].re;
-    for(size_t k = (size_t)blockIdx.x * VB_T + threadIdx.x; k < n; k += (size_t)VB_BLOCKS * VB_T) p[k] = r[k] + beta * p[k];
-    if(blockIdx.x == 0 && threadIdx.x == 0) scal[2] = cplx(rs_new, 0.0);
+                                                  const cplx* __restrict__ part_rr, const double* __restrict__ minv, size_t n) {
+    const cplx rs_new = sum_partials(part_rr);
+    const double beta = rs_new.re / scal[0].re;
+    for(size_t k = (size_t)blockIdx.x * VB_T + threadIdx.x; k < n; k += (size_t)VB_BLOCKS * VB_T) {
+        const cplx z = minv ? minv[k] * r[k] : r[k];
+        p[k] = z + beta * p[k];
+    }
+    if(blockIdx.x == 0 && threadIdx.x == 0) scal[2] = rs_new;
+}
+// start of the iteration: p = z = minv * r (or r); scal0 = (r.z, |r|^2).  One block (runs once per solve).
+__global__ void __launch_bounds__(RED_T) k_cg_init(cplx* __restrict__ p, const cplx* __restrict__ r, const double* __restrict__ minv, size_t n, cplx* scal0) {
+    double v[2] = {0, 0}, red[2];
+    for(size_t k = threadIdx.x; k < n; k += RED_T) {
+        const cplx rk = r[k];
+        const double a2 = abs2(rk);
+        p[k] = minv ? minv[k] * rk : rk;
+        v[1] += a2; v[0] += minv ? minv[k] * a2 : a2;
+    }
+    block_reduce<2>(v, red);
+    if(threadIdx.x == 0) *scal0 = cplx(red[0], red[1]);
+}
+// minv_k = 1 / (diag_k + shift_abs + shift_rel * diag_k): the inverse diagonal of the shifted S
+__global__ void k_jacobi_inverse(const double* __restrict__ diag, double shift_abs, double shift_rel, size_t n, double* __restrict__ minv) {
+    for(size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+        const double m = diag[k] + shift_abs + shift_rel * diag[k];
+        minv[k] = m > 0.0 ? 1.0 / m : 1.0;
+    }
 }
 
 // ============================================================================================ solver kernels
@@ -1052,8 +1047,18 @@ int TDVP::solve_cg(double tol, unsigned max_iter, double shift_abs, double shift
     const bool use_S = have_S && !factorised && !force_free;
     mark(5);
     const size_t n = P;
-    DevBuf<double> dg;
-    if(shift_rel != 0.0) tdvp_diag(*this, dg); else { dg.resize(n); dg.zero(); }
+    // Jacobi preconditioning (M = diagonal of the shifted S) is the default; ANGPU_CG_PRECOND=none gives plain CG
+    const char* env_pc = getenv("ANGPU_CG_PRECOND");
+    const bool jacobi = !(env_pc && std::string(env_pc) == "none");
+    DevBuf<double> dg, minv_buf;
+    if(shift_rel != 0.0 || jacobi) tdvp_diag(*this, dg); else { dg.resize(n); dg.zero(); }
+    const double* minv = nullptr;
+    if(jacobi) {
+        minv_buf.resize(n);
+        k_jacobi_inverse<<<grid_for(n), 256, 0, stream()>>>(dg.p, shift_abs, shift_rel, n, minv_buf.p);
+        ANGPU_CHECK_LAUNCH(); count_launch();
+        minv = minv_buf.p;
+    }
     cg_buf.resize(5 * n);                                     // x | r | p | Ap | b
     cplx *x = cg_buf.p, *r = x + n, *p = r + n, *Ap = p + n, *b = Ap + n;
     d_scal.resize(16);
@@ -1061,13 +1066,12 @@ int TDVP::solve_cg(double tol, unsigned max_iter, double shift_abs, double shift
     ANGPU_CUDA(cudaMemsetAsync(x, 0, sizeof(cplx) * n, stream()));
     k_scale_vec<<<grid_for(n), 256, 0, stream()>>>(F.p, rhs_phase, b, n, false);
     ANGPU_CUDA(cudaMemcpyAsync(r, b, sizeof(cplx) * n, cudaMemcpyDeviceToDevice, stream()));
-    ANGPU_CUDA(cudaMemcpyAsync(p, b, sizeof(cplx) * n, cudaMemcpyDeviceToDevice, stream()));
-    k_dot<true><<<1, RED_T, 0, stream()>>>(r, r, n, scal + 0);
-    count_launch(2);
+    k_cg_init<<<1, RED_T, 0, stream()>>>(p, r, minv, n, scal + 0);
+    ANGPU_CHECK_LAUNCH(); count_launch(2);
     // convergence is decided on values summed over ranks, so that every rank takes the same decision
-    auto read_rs = [&](int slot) -> double {
+    auto read_rs = [&](int slot) -> double {      // |r|^2 = the imaginary slot of the (r.z, |r|^2) pair
         double* chk = d_scal.p + 12;
-        ANGPU_CUDA(cudaMemcpyAsync(chk, scal + slot, sizeof(double), cudaMemcpyDeviceToDevice, stream()));
+        ANGPU_CUDA(cudaMemcpyAsync(chk, reinterpret_cast<double*>(scal + slot) + 1, sizeof(double), cudaMemcpyDeviceToDevice, stream()));
         allreduce_sum(chk, 1);
         double hv = 0.0;
         ANGPU_CUDA(cudaMemcpyAsync(&hv, chk, sizeof(double), cudaMemcpyDeviceToHost, stream()));
@@ -1080,24 +1084,18 @@ int TDVP::solve_cg(double tol, unsigned max_iter, double shift_abs, double shift
     unsigned it = 0;
     if(b2 > 0.0) {
         const unsigned check_every = 8;
-        const bool fused = false;      // the multi-block vector kernels (3 x ~5 us) beat the single-block fused one (~40 us at P = 16k)
-        if(fused) { k_dot<false><<<1, RED_T, 0, stream()>>>(Ok_dev(), p, n, scal + 3); ANGPU_CHECK_LAUNCH(); count_launch(); }
         for(it = 1; it <= max_iter; it++) {
-            if(fused) {
-                matvec(p, Ap, scal + 3, dg.p, shift_abs, shift_rel);
-                k_cg_fused<<<1, RED_T, 0, stream()>>>(x, r, p, Ap, Ok_dev(), scal, n);
-                ANGPU_CHECK_LAUNCH(); count_launch();
-            } else {
+            {
                 matvec(p, Ap, nullptr, dg.p, shift_abs, shift_rel, use_S);
                 vb_part.resize(3 * VB_BLOCKS);
                 cplx* part_pAp = vb_part.p; cplx* part_rr = vb_part.p + VB_BLOCKS;
                 k_dot_part<true><<<VB_BLOCKS, VB_T, 0, stream()>>>(p, Ap, n, part_pAp, it > 1 ? scal : nullptr);
-                k_cg_xr_mb<<<VB_BLOCKS, VB_T, 0, stream()>>>(x, r, p, Ap, scal, part_pAp, part_rr, n);
-                k_cg_p_mb<<<VB_BLOCKS, VB_T, 0, stream()>>>(p, r, scal, part_rr, n);
+                k_cg_xr_mb<<<VB_BLOCKS, VB_T, 0, stream()>>>(x, r, p, Ap, scal, part_pAp, part_rr, minv, n);
+                k_cg_p_mb<<<VB_BLOCKS, VB_T, 0, stream()>>>(p, r, scal, part_rr, minv, n);
                 ANGPU_CHECK_LAUNCH(); count_launch(3);
             }
             if(it % check_every == 0 || it == max_iter) {
-                h.re = read_rs(fused ? 0 : 2);
+                h.re = read_rs(2);
                 if(rel_res_out) *rel_res_out = std::sqrt(h.re / b2);
                 if(h.re <= tol * tol * b2) break;
             }
