@@ -568,6 +568,21 @@ __device__ __forceinline__ cplx sum_partials(const cplx* part) {
     for(int b = 0; b < VB_BLOCKS; b++) t += part[b];
     return t;
 }
+// the same sum computed once per block by its first warp (fixed order: lane-strided, then the shuffle tree) and broadcast;
+// every thread of the block must call it
+__device__ __forceinline__ cplx sum_partials_block(const cplx* part) {
+    __shared__ cplx bc;
+    if(threadIdx.x < 32u) {
+        cplx t(0.0, 0.0);
+        for(int b = (int)threadIdx.x; b < VB_BLOCKS; b += 32) t += part[b];
+        t = warp_sum(t);
+        if(threadIdx.x == 0) bc = t;
+    }
+    __syncthreads();
+    const cplx r = bc;
+    __syncthreads();
+    return r;
+}
 // part[b] = sum over the block's elements of op(a) b
 template<bool CONJ_A>
 __global__ void __launch_bounds__(VB_T) k_dot_part(const cplx* __restrict__ a, const cplx* __restrict__ b, size_t n, cplx* __restrict__ part,
@@ -589,7 +604,7 @@ __global__ void k_sum_part_to_scalar(const cplx* __restrict__ part, cplx* out) {
 __global__ void __launch_bounds__(VB_T) k_cg_xr_mb(cplx* __restrict__ x, cplx* __restrict__ r, const cplx* __restrict__ p, const cplx* __restrict__ Ap,
                                                    const cplx* __restrict__ scal, const cplx* __restrict__ part_pAp, cplx* __restrict__ part_rr,
                                                    const double* __restrict__ minv, size_t n) {
-    const double alpha = scal[0].re / sum_partials(part_pAp).re;
+    const double alpha = scal[0].re / sum_partials_block(part_pAp).re;
     double v[2] = {0, 0}, red[2];
     for(size_t k = (size_t)blockIdx.x * VB_T + threadIdx.x; k < n; k += (size_t)VB_BLOCKS * VB_T) {
         x[k] += alpha * p[k];
@@ -602,28 +617,62 @@ __global__ void __launch_bounds__(VB_T) k_cg_xr_mb(cplx* __restrict__ x, cplx* _
     block_reduce_small<2>(v, red);
     if(threadIdx.x == 0) part_rr[blockIdx.x] = cplx(red[0], red[1]);
 }
-// (rz_new, rr_new) = sum(part_rr); beta = rz_new / rz; p = z + beta p; scal[2] = (rz_new, rr_new)
+// (rz_new, rr_new) = sum(part_rr); beta = rz_new / rz; p = z + beta p; scal[2] = (rz_new, rr_new);
+// part_dot[b] (optional) = partial sums of Obar . p_new, the scalar the next S.v needs
 __global__ void __launch_bounds__(VB_T) k_cg_p_mb(cplx* __restrict__ p, const cplx* __restrict__ r, cplx* __restrict__ scal,
-                                                  const cplx* __restrict__ part_rr, const double* __restrict__ minv, size_t n) {
-    const cplx rs_new = sum_partials(part_rr);
+                                                  const cplx* __restrict__ part_rr, const double* __restrict__ minv,
+                                                  const cplx* __restrict__ Obar, cplx* __restrict__ part_dot, size_t n) {
+    const cplx rs_new = sum_partials_block(part_rr);
     const double beta = rs_new.re / scal[0].re;
+    double v[2] = {0, 0}, red[2];
     for(size_t k = (size_t)blockIdx.x * VB_T + threadIdx.x; k < n; k += (size_t)VB_BLOCKS * VB_T) {
         const cplx z = minv ? minv[k] * r[k] : r[k];
-        p[k] = z + beta * p[k];
+        const cplx pk = z + beta * p[k];
+        p[k] = pk;
+        if(part_dot) { const cplx d = Obar[k] * pk; v[0] += d.re; v[1] += d.im; }
+    }
+    if(part_dot) {
+        block_reduce_small<2>(v, red);
+        if(threadIdx.x == 0) part_dot[blockIdx.x] = cplx(red[0], red[1]);
     }
     if(blockIdx.x == 0 && threadIdx.x == 0) scal[2] = rs_new;
 }
+// S.v epilogue fused with the CG scalar work: Ap = sum of the column-reduction chunks - conj(Obar) (Obar . p) + shift p,
+// part_pAp[b] = partial sums of conj(p) . Ap; rolls (r.z, |r|^2) of the previous iteration into scal[0]
+__global__ void __launch_bounds__(VB_T) k_sv_finish_cg(const cplx* __restrict__ part, unsigned chunks, const cplx* __restrict__ Obar,
+        const cplx* __restrict__ part_dot, const cplx* __restrict__ v, const double* __restrict__ diag, double shift_abs, double shift_rel,
+        size_t P, cplx* __restrict__ out, cplx* __restrict__ part_pAp, cplx* scal_roll) {
+    if(scal_roll && blockIdx.x == 0 && threadIdx.x == 0) scal_roll[0] = scal_roll[2];
+    const cplx d = sum_partials_block(part_dot);
+    double acc[2] = {0, 0}, red[2];
+    for(size_t k = (size_t)blockIdx.x * VB_T + threadIdx.x; k < P; k += (size_t)VB_BLOCKS * VB_T) {
+        cplx a(0.0, 0.0);
+        for(unsigned c = 0; c < chunks; c++) a += part[(size_t)c * P + k];
+        a -= conj(Obar[k]) * d;
+        const cplx vk = v[k];
+        a += (shift_abs + shift_rel * diag[k]) * vk;
+        out[k] = a;
+        const cplx q = conj(vk) * a;
+        acc[0] += q.re; acc[1] += q.im;
+    }
+    block_reduce_small<2>(acc, red);
+    if(threadIdx.x == 0) part_pAp[blockIdx.x] = cplx(red[0], red[1]);
+}
 // start of the iteration: p = z = minv * r (or r); scal0 = (r.z, |r|^2).  One block (runs once per solve).
-__global__ void __launch_bounds__(RED_T) k_cg_init(cplx* __restrict__ p, const cplx* __restrict__ r, const double* __restrict__ minv, size_t n, cplx* scal0) {
-    double v[2] = {0, 0}, red[2];
+__global__ void __launch_bounds__(RED_T) k_cg_init(cplx* __restrict__ p, const cplx* __restrict__ r, const double* __restrict__ minv, size_t n, cplx* scal0,
+                                                   const cplx* __restrict__ Obar, cplx* __restrict__ part_dot) {
+    double v[4] = {0, 0, 0, 0}, red[4];
     for(size_t k = threadIdx.x; k < n; k += RED_T) {
         const cplx rk = r[k];
         const double a2 = abs2(rk);
-        p[k] = minv ? minv[k] * rk : rk;
+        const cplx pk = minv ? minv[k] * rk : rk;
+        p[k] = pk;
         v[1] += a2; v[0] += minv ? minv[k] * a2 : a2;
+        const cplx d = Obar[k] * pk; v[2] += d.re; v[3] += d.im;
     }
-    block_reduce<2>(v, red);
-    if(threadIdx.x == 0) *scal0 = cplx(red[0], red[1]);
+    block_reduce<4>(v, red);
+    if(threadIdx.x == 0) { *scal0 = cplx(red[0], red[1]); part_dot[0] = cplx(red[2], red[3]); }
+    for(int b = 1 + (int)threadIdx.x; b < VB_BLOCKS; b += RED_T) part_dot[b] = cplx(0.0, 0.0);
 }
 // minv_k = 1 / (diag_k + shift_abs + shift_rel * diag_k): the inverse diagonal of the shifted S
 __global__ void k_jacobi_inverse(const double* __restrict__ diag, double shift_abs, double shift_rel, size_t n, double* __restrict__ minv) {
@@ -969,6 +1018,20 @@ void TDVP::build_S() {
     if(profile) { ANGPU_CUDA(cudaEventSynchronize(ev[6])); ANGPU_CUDA(cudaEventElapsedTime(&phase_ms[4], ev[5], ev[6])); }
 }
 
+// row_a[s] = O_s . v over the local samples
+void TDVP::rowdot(const cplx* v_dev) {
+    const size_t ns = S.ns;
+    row_a.resize(std::max<size_t>(1, ns));
+    if(!ns) return;
+    if(factorised && use_dmma()) {
+        static bool attr_set = false;
+        if(!attr_set) { ANGPU_CUDA(cudaFuncSetAttribute(k_rowdot_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RD_SMEM)); attr_set = true; }
+        k_rowdot_dmma<<<ceil_div(ns, RD_WARPS * 8), RD_WARPS * 32, RD_SMEM, stream()>>>(S.conf.p, T.p, v_dev, ns, rbm_N, rbm_M, words, row_a.p);
+    }
+    else if(factorised) k_rowdot_rbm<<<ceil_div(ns, RBM_ST), 256, 0, stream()>>>(S.conf.p, T.p, v_dev, ns, rbm_N, rbm_M, words, row_a.p);
+    else k_rowdot_dense<<<(unsigned)ns, 256, 0, stream()>>>(O.p, v_dev, P, row_a.p);
+    ANGPU_CHECK_LAUNCH(); count_launch();
+}
 // out = S v (+ (shift_abs + shift_rel diag) v when diag != null).  dot_dev: device scalar Obar . v if already known.
 void TDVP::matvec(const cplx* v_dev, cplx* out_dev, const cplx* dot_dev, const double* diag, double shift_abs, double shift_rel, bool allow_S) {
     ANGPU_REQUIRE(evaluated, "TDVP: call eval / eval_F first");
@@ -977,18 +1040,7 @@ void TDVP::matvec(const cplx* v_dev, cplx* out_dev, const cplx* dot_dev, const d
         ANGPU_CHECK_LAUNCH(); count_launch();
         return;
     }
-    const size_t ns = S.ns;
-    row_a.resize(std::max<size_t>(1, ns));
-    if(ns) {
-        if(factorised && use_dmma()) {
-            static bool attr_set = false;
-            if(!attr_set) { ANGPU_CUDA(cudaFuncSetAttribute(k_rowdot_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RD_SMEM)); attr_set = true; }
-            k_rowdot_dmma<<<ceil_div(ns, RD_WARPS * 8), RD_WARPS * 32, RD_SMEM, stream()>>>(S.conf.p, T.p, v_dev, ns, rbm_N, rbm_M, words, row_a.p);
-        }
-        else if(factorised) k_rowdot_rbm<<<ceil_div(ns, RBM_ST), 256, 0, stream()>>>(S.conf.p, T.p, v_dev, ns, rbm_N, rbm_M, words, row_a.p);
-        else k_rowdot_dense<<<(unsigned)ns, 256, 0, stream()>>>(O.p, v_dev, P, row_a.p);
-        ANGPU_CHECK_LAUNCH(); count_launch();
-    }
+    rowdot(v_dev);
     d_scal.resize(16);
     if(!dot_dev) {
         cplx* dot = reinterpret_cast<cplx*>(d_scal.p) + 4;
@@ -1066,8 +1118,14 @@ int TDVP::solve_cg(double tol, unsigned max_iter, double shift_abs, double shift
     ANGPU_CUDA(cudaMemsetAsync(x, 0, sizeof(cplx) * n, stream()));
     k_scale_vec<<<grid_for(n), 256, 0, stream()>>>(F.p, rhs_phase, b, n, false);
     ANGPU_CUDA(cudaMemcpyAsync(r, b, sizeof(cplx) * n, cudaMemcpyDeviceToDevice, stream()));
-    k_cg_init<<<1, RED_T, 0, stream()>>>(p, r, minv, n, scal + 0);
+    vb_part.resize(3 * VB_BLOCKS);
+    cplx* part_pAp = vb_part.p; cplx* part_rr = vb_part.p + VB_BLOCKS; cplx* part_dot = vb_part.p + 2 * VB_BLOCKS;
+    k_cg_init<<<1, RED_T, 0, stream()>>>(p, r, minv, n, scal + 0, Ok_dev(), part_dot);
     ANGPU_CHECK_LAUNCH(); count_launch(2);
+    // single process, sample-based products: the S.v epilogue, p.Ap, |r|^2 and Obar.p ride in three fused vector kernels
+    // (5 launches per iteration); otherwise (all-reduce between the halves of S.v, or products on the dense S) the
+    // generic matvec + separate dot product is used
+    const bool fused = !has_allreduce() && !use_S && S.ns > 0;
     // convergence is decided on values summed over ranks, so that every rank takes the same decision
     auto read_rs = [&](int slot) -> double {      // |r|^2 = the imaginary slot of the (r.z, |r|^2) pair
         double* chk = d_scal.p + 12;
@@ -1085,13 +1143,19 @@ int TDVP::solve_cg(double tol, unsigned max_iter, double shift_abs, double shift
     if(b2 > 0.0) {
         const unsigned check_every = 8;
         for(it = 1; it <= max_iter; it++) {
-            {
+            if(fused) {
+                rowdot(p);
+                const ColPartials cp = col_reduce_partials(*this, row_a.p, false);
+                k_sv_finish_cg<<<VB_BLOCKS, VB_T, 0, stream()>>>(cp.x, cp.chunks, Ok_dev(), part_dot, p, dg.p, shift_abs, shift_rel, n, Ap,
+                                                                  part_pAp, it > 1 ? scal : nullptr);
+                k_cg_xr_mb<<<VB_BLOCKS, VB_T, 0, stream()>>>(x, r, p, Ap, scal, part_pAp, part_rr, minv, n);
+                k_cg_p_mb<<<VB_BLOCKS, VB_T, 0, stream()>>>(p, r, scal, part_rr, minv, Ok_dev(), part_dot, n);
+                ANGPU_CHECK_LAUNCH(); count_launch(3);
+            } else {
                 matvec(p, Ap, nullptr, dg.p, shift_abs, shift_rel, use_S);
-                vb_part.resize(3 * VB_BLOCKS);
-                cplx* part_pAp = vb_part.p; cplx* part_rr = vb_part.p + VB_BLOCKS;
                 k_dot_part<true><<<VB_BLOCKS, VB_T, 0, stream()>>>(p, Ap, n, part_pAp, it > 1 ? scal : nullptr);
                 k_cg_xr_mb<<<VB_BLOCKS, VB_T, 0, stream()>>>(x, r, p, Ap, scal, part_pAp, part_rr, minv, n);
-                k_cg_p_mb<<<VB_BLOCKS, VB_T, 0, stream()>>>(p, r, scal, part_rr, minv, n);
+                k_cg_p_mb<<<VB_BLOCKS, VB_T, 0, stream()>>>(p, r, scal, part_rr, minv, nullptr, nullptr, n);
                 ANGPU_CHECK_LAUNCH(); count_launch(3);
             }
             if(it % check_every == 0 || it == max_iter) {

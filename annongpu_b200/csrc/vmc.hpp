@@ -97,6 +97,7 @@ struct TDVP {
     void ensure_dense_O(Psi* psi);
     // out = S v using the samples of the last eval (TDVP::S_dot_vector, :337-443), O(ns*P) instead of the reference's O(ns*P^2)
     void S_dot_vector_dev(const cplx* v_dev, cplx* out_dev);
+    void rowdot(const cplx* v_dev);
     void matvec(const cplx* v_dev, cplx* out_dev, const cplx* dot_dev, const double* diag, double shift_abs, double shift_rel, bool allow_S = false);
     void S_dot_vector(const cplx* v_host, cplx* out_host);
     // NEW (no reference counterpart): solve (S + shift_abs*I + shift_rel*diag(S)) x = rhs_phase * F
