@@ -320,11 +320,16 @@ class PsiRBM(_Psi):
         return self.params.reshape(self.N, self.M)
 
     def to_json(self):
-        return dict(type="PsiRBM", W=self.W, final_weight=self.final_weight,
-                    log_prefactor_re=self.log_prefactor.real, log_prefactor_im=self.log_prefactor.imag)
+        """pyANNonGPU/PsiRBM.py:7-19 (same keys and array encoding)."""
+        from .json_numpy import plain
+        fw = self.final_weight
+        return plain(dict(type="PsiRBM", W=self.W, final_weight=fw.real if fw.imag == 0.0 else fw,
+                          log_prefactor_re=self.log_prefactor.real, log_prefactor_im=self.log_prefactor.imag))
 
     @staticmethod
-    def from_json(obj, gpu=True):
+    def from_json(json_obj, gpu=True):
+        from .json_numpy import restore
+        obj = restore(json_obj)
         return PsiRBM(np.asarray(obj["W"]), obj["final_weight"], obj["log_prefactor_re"] + 1j * obj["log_prefactor_im"], gpu)
 
 
@@ -377,6 +382,25 @@ class PsiDeep(_Psi):
         return self._final_weights.copy()
 
 
+def _deep_to_json(self):
+    """pyANNonGPU/PsiDeep.py:7-22 (same keys and array encoding)."""
+    from .json_numpy import plain
+    return plain(dict(type="PsiDeep", num_sites=self.num_sites, a=self.a, b=list(self.b), connections=list(self.connections),
+                      W=list(self.W), final_weights=self.final_weights,
+                      log_prefactor_re=self.log_prefactor.real, log_prefactor_im=self.log_prefactor.imag))
+
+
+def _deep_from_json(json_obj, gpu=True):
+    from .json_numpy import restore
+    obj = restore(json_obj)
+    return PsiDeep(obj["num_sites"], obj["a"], obj["b"], obj["connections"], obj["W"], obj["final_weights"],
+                   obj["log_prefactor_re"] + 1j * obj["log_prefactor_im"], gpu)
+
+
+PsiDeep.to_json = _deep_to_json
+PsiDeep.from_json = staticmethod(_deep_from_json)
+
+
 class PsiCNN(_Psi):
     """PsiCNN(extent, num_channels_list, connectivity_list, symmetry_classes, params, final_factor, log_prefactor, gpu)
     (pyANNonGPU/main.cpp.template:160-204)."""
@@ -416,6 +440,26 @@ class PsiCNN(_Psi):
                 off += (prev_channel * nch + channel) * self.num_symmetry_classes * vol
                 return self.params[off:off + self.num_symmetry_classes * vol].reshape(self.num_symmetry_classes, vol)
             off += nch * prev * self.num_symmetry_classes * vol
+
+
+def _cnn_to_json(self):
+    """pyANNonGPU/PsiCNN.py:7-23 (same keys and array encoding)."""
+    from .json_numpy import plain
+    return plain(dict(type="PsiCNN", extent=np.asarray(self.extent), num_channels_list=np.asarray(self.num_channels_list),
+                      connectivity_list=np.asarray(self.connectivity_list), symmetry_classes=np.asarray(self.symmetry_classes),
+                      params=self.params, final_factor=self.final_factor,
+                      log_prefactor_re=self.log_prefactor.real, log_prefactor_im=self.log_prefactor.imag))
+
+
+def _cnn_from_json(json_obj, gpu=True):
+    from .json_numpy import restore
+    obj = restore(json_obj)
+    return PsiCNN(obj["extent"], obj["num_channels_list"], obj["connectivity_list"], obj["symmetry_classes"], obj["params"],
+                  obj["final_factor"], obj["log_prefactor_re"] + 1j * obj["log_prefactor_im"], gpu)
+
+
+PsiCNN.to_json = _cnn_to_json
+PsiCNN.from_json = staticmethod(_cnn_from_json)
 
 
 class PsiFullyPolarized:

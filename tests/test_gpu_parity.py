@@ -505,3 +505,21 @@ def test_cnn_incremental_sampler_bit_identical_to_full_forward(gpu, name):
     assert np.array_equal(out["incremental"][0], out["generic"][0])
     assert np.array_equal(out["incremental"][1], out["generic"][1])
     assert out["incremental"][2] == out["generic"][2]
+
+
+# ------------------------------------------------------------------------------------------------ SURVEY 8f rank 4 (wire format)
+
+@pytest.mark.parametrize("name", ["rbm8_cfw", "deep3", "cnn_sym"])
+def test_json_round_trip(gpu, name):
+    """psi.to_json() (the reference's key names and ndarray encoding, pyANNonGPU/Psi*.py) survives json.dumps/loads and
+    rebuilds a state with identical parameters and amplitudes."""
+    import json
+    spec, H, N = zoo()[name]
+    psi = make_psi(gpu, spec)
+    psi.log_prefactor = 0.3 - 0.2j
+    obj = json.loads(json.dumps(psi.to_json()))
+    assert obj["type"] == type(psi).__name__
+    psi2 = type(psi).from_json(obj, True)
+    assert np.array_equal(psi2.params, psi.params) and psi2.log_prefactor == psi.log_prefactor
+    es = gpu.ExactSummationSpins(N)
+    assert np.array_equal(gpu.log_psi_vector(psi2, es), gpu.log_psi_vector(psi, es))
