@@ -142,7 +142,7 @@ def run_reference(args):
                                    "unmodified reference cannot run M=256 (PsiRBM::max_N=128)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -274,11 +274,30 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": n / times[0], "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{n} of the {chains_local} chains (same per-chain work: {THERM}+{SWEEPS} sweeps, E_loc, O_k), "
                                               f"one call, {times[0]:.1f} s, OpenMP over chains"}
-        print(json.dumps(line))
+        emit(line)
     D.shutdown()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract, written to the process' original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # libraries (NCCL prints its version banner to stdout) must not pollute the one-line contract: everything written to
+    # fd 1 while the benchmark runs goes to stderr; the JSON line is written to the saved descriptor at the end
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
