@@ -245,7 +245,11 @@ def run_ours(args):
     hbm_peak, peak_src = measured_peaks()
     fp64_peak = A.measure_fp64_tflops()
     roofline = {"kernel": "k_mc_rbm<8,true>", "bound": "hbm", "achieved": hbm_bytes / t_sample / 1e9, "peak": hbm_peak,
-                "unit": "GB/s", "frac": hbm_bytes / t_sample / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": hbm_bytes / t_sample / 1e9 / hbm_peak,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 8192 chains, from the ncu --set full capture
+                # profiles/r01_ncu_full_sampler_eloc_after_tuning.csv (0.281 MB + 0.047 MB): BELOW the algorithmic bytes
+                # because the 34 MB of outputs stay in the 126 MB L2 until the consumers read them
+                "traffic": 0.328e6 if chains_local == 8192 else None, "algorithmic_bytes": hbm_bytes, "peak_source": peak_src,
                 "note": "the sampler is FP64-pipe bound by design (W and the angle cache stay on chip, SURVEY.md §8d): "
                         "see roofline_fp64 for the binding roof"}
     roofline_fp64 = {"kernel": "k_mc_rbm<8,true>", "bound": "fp64", "achieved": flops / t_sample / 1e12, "peak": fp64_peak,
