@@ -25,48 +25,12 @@ struct CnnIncDev {
     unsigned        backup_elems;             // sum_l nch_l * aff_max[l]
 };
 
-// per-warp scratch: act[num_angles] | backup[backup_elems]   (complex)
+// per-warp scratch: act[num_angles] | backup[backup_elems] (complex) | spin[N] (double, padded to 16 B)
 __host__ __device__ inline size_t cnn_inc_slice_bytes(const CnnDev& psi, const CnnIncDev& inc) {
-    return (size_t)(psi.num_angles + inc.backup_elems) * sizeof(cplx);
+    return (size_t)(psi.num_angles + inc.backup_elems) * sizeof(cplx) + (((size_t)psi.N * sizeof(double) + 15u) & ~(size_t)15u);
 }
 
 #ifdef __CUDACC__
-
-// all NCH outputs of layer l at site x, from the layer's input (spins for l == 0, else the previous layer's activations)
-template<int NCH>
-__device__ __forceinline__ void cnn_site_outputs(const CnnDev& psi, const CnnLayerDev& ly, unsigned l, const cplx* __restrict__ wgt,
-                                                 const uint64_t (&conf)[MAXW], const cplx* in, unsigned x, cplx* out) {
-    const unsigned N = psi.N;
-    const unsigned* nb = ly.nbr + x * ly.vol;
-    const cplx* wq = wgt + ly.begin_params + (size_t)psi.sym[x] * ly.vol * ly.prev * NCH;
-    cplx acc[NCH];
-    #pragma unroll
-    for(int cj = 0; cj < NCH; cj++) acc[cj] = cplx(0.0, 0.0);
-    for(unsigned c = 0; c < ly.vol; c++) {
-        const unsigned src = nb[c];
-        for(unsigned ci = 0; ci < ly.prev; ci++) {
-            const cplx sv = (l == 0u) ? cplx(conf_spin(conf, src), 0.0) : in[ci * N + src];
-            #pragma unroll
-            for(int cj = 0; cj < NCH; cj++) cfma(acc[cj], wq[cj], sv);
-            wq += NCH;
-        }
-    }
-    #pragma unroll
-    for(int cj = 0; cj < NCH; cj++) out[(unsigned)cj * N + x] = act_lc(acc[cj], l);
-}
-__device__ __forceinline__ void cnn_site_outputs_any(const CnnDev& psi, const CnnLayerDev& ly, unsigned l, const cplx* __restrict__ wgt,
-                                                     const uint64_t (&conf)[MAXW], const cplx* in, unsigned x, cplx* out) {
-    switch(ly.nch) {
-        case 1: cnn_site_outputs<1>(psi, ly, l, wgt, conf, in, x, out); break;
-        case 2: cnn_site_outputs<2>(psi, ly, l, wgt, conf, in, x, out); break;
-        case 3: cnn_site_outputs<3>(psi, ly, l, wgt, conf, in, x, out); break;
-        case 4: cnn_site_outputs<4>(psi, ly, l, wgt, conf, in, x, out); break;
-        case 5: cnn_site_outputs<5>(psi, ly, l, wgt, conf, in, x, out); break;
-        case 6: cnn_site_outputs<6>(psi, ly, l, wgt, conf, in, x, out); break;
-        case 7: cnn_site_outputs<7>(psi, ly, l, wgt, conf, in, x, out); break;
-        default: cnn_site_outputs<8>(psi, ly, l, wgt, conf, in, x, out); break;
-    }
-}
 
 __global__ void __launch_bounds__(128)
 k_mc_cnn_inc(const CnnDev psi, const CnnIncDev inc, const McParams mc, uint64_t* __restrict__ conf_out,
@@ -78,6 +42,7 @@ k_mc_cnn_inc(const CnnDev psi, const CnnIncDev inc, const McParams mc, uint64_t*
     const cplx* __restrict__ wgt = reinterpret_cast<const cplx*>(psi.stage(smem_raw + (size_t)wpb * slice));
     cplx* act = reinterpret_cast<cplx*>(smem_raw + (size_t)warp * slice);
     cplx* backup = act + psi.num_angles;
+    double* spin = reinterpret_cast<double*>(backup + inc.backup_elems);       // the configuration as +-1.0 (layer-0 input)
     const unsigned chain = blockIdx.x * wpb + warp;
     if(chain >= mc.num_chains_local) return;
     const unsigned gchain = mc.chain0 + chain, N = psi.N, NL = psi.num_layers;
@@ -93,11 +58,13 @@ k_mc_cnn_inc(const CnnDev psi, const CnnIncDev inc, const McParams mc, uint64_t*
             if(w == psi.words - 1u && (N & 63u)) conf[w] &= (1ull << (N & 63u)) - 1ull;
         }
     }
+    for(unsigned x = lane; x < N; x += 32u) spin[x] = conf_spin(conf, x);
+    __syncwarp();
     // full forward pass (forward_pass, PsiCNN.hpp:99-160)
     for(unsigned l = 0; l < NL; l++) {
         const CnnLayerDev& ly = psi.L[l];
         const cplx* in = l ? act + psi.L[l - 1u].angle_off : nullptr;
-        for(unsigned x = lane; x < N; x += 32u) cnn_site_outputs_any(psi, ly, l, wgt, conf, in, x, act + ly.angle_off);
+        for(unsigned x = lane; x < N; x += 32u) psi.site_outputs_any(ly, l, wgt, in, spin, x, act + ly.angle_off, nullptr);
         __syncwarp();
     }
     const CnnLayerDev& last = psi.L[NL - 1u];
@@ -122,6 +89,8 @@ k_mc_cnn_inc(const CnnDev psi, const CnnIncDev inc, const McParams mc, uint64_t*
             const unsigned site = __shfl_sync(FULL, my_site, b);
             const double u = u01_from_bits(__shfl_sync(FULL, my_ulo, b), __shfl_sync(FULL, my_uhi, b));
             conf_flip(conf, site);
+            if(lane == 0) spin[site] = -spin[site];
+            __syncwarp();
             // recompute the receptive cone of `site` in place, layer by layer, keeping the old values
             unsigned boff = 0;
             for(unsigned l = 0; l < NL; l++) {
@@ -133,7 +102,7 @@ k_mc_cnn_inc(const CnnDev psi, const CnnIncDev inc, const McParams mc, uint64_t*
                 for(unsigned k = lane; k < cnt; k += 32u) {
                     const unsigned x = list[k];
                     for(unsigned cj = 0; cj < ly.nch; cj++) backup[boff + cj * inc.aff_max[l] + k] = out[cj * N + x];
-                    cnn_site_outputs_any(psi, ly, l, wgt, conf, in, x, out);
+                    psi.site_outputs_any(ly, l, wgt, in, spin, x, out, nullptr);
                 }
                 boff += ly.nch * inc.aff_max[l];
                 __syncwarp();
@@ -144,6 +113,7 @@ k_mc_cnn_inc(const CnnDev psi, const CnnIncDev inc, const McParams mc, uint64_t*
                 acc++;
             } else {
                 conf_flip(conf, site);
+                if(lane == 0) spin[site] = -spin[site];
                 boff = 0;
                 for(unsigned l = 0; l < NL; l++) {
                     const CnnLayerDev& ly = psi.L[l];

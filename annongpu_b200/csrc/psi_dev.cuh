@@ -239,9 +239,82 @@ struct CnnDev {
         return blk;
     }
     __device__ void init(const uint64_t*, cplx*, const unsigned char* = nullptr) const {}
+    // All NCH outputs of layer l at site x from staged weights (see stage()): the one routine behind the full forward pass
+    // and the incremental sampler (cnn_kernels.cuh), so both produce bit-identical activations.  PREV = input channels
+    // (compile time, 0 = run-time loop); FIRST = layer 0, whose inputs are the real spins: only the two FMAs with a
+    // non-zero factor are issued (the omitted ones add w * 0).  in_real (optional, FIRST only): spins as doubles.
+    template<int NCH, int PREV, bool FIRST>
+    __device__ __forceinline__ void site_outputs(const CnnLayerDev& ly, unsigned l, const cplx* __restrict__ wgt, const cplx* in,
+                                                 const double* in_real, unsigned x, cplx* out, cplx* angles) const {
+        const unsigned* nb = ly.nbr + x * ly.vol;
+        const unsigned prev = PREV ? (unsigned)PREV : ly.prev;
+        const cplx* wq = wgt + ly.begin_params + (size_t)sym[x] * ly.vol * prev * NCH;
+        cplx acc[NCH];
+        #pragma unroll
+        for(int cj = 0; cj < NCH; cj++) acc[cj] = cplx(0.0, 0.0);
+        #pragma unroll 3
+        for(unsigned c = 0; c < ly.vol; c++) {
+            const unsigned src = nb[c];
+            if(FIRST) {
+                const double sv = in_real ? in_real[src] : in[src].re;
+                #pragma unroll
+                for(int cj = 0; cj < NCH; cj++) { acc[cj].re = fma(wq[cj].re, sv, acc[cj].re); acc[cj].im = fma(wq[cj].im, sv, acc[cj].im); }
+                wq += NCH;
+            } else if(PREV) {
+                #pragma unroll
+                for(int ci = 0; ci < (PREV ? PREV : 1); ci++) {
+                    const cplx sv = in[(unsigned)ci * N + src];
+                    #pragma unroll
+                    for(int cj = 0; cj < NCH; cj++) cfma(acc[cj], wq[cj], sv);
+                    wq += NCH;
+                }
+            } else {
+                for(unsigned ci = 0; ci < prev; ci++) {
+                    const cplx sv = in[ci * N + src];
+                    #pragma unroll
+                    for(int cj = 0; cj < NCH; cj++) cfma(acc[cj], wq[cj], sv);
+                    wq += NCH;
+                }
+            }
+        }
+        #pragma unroll
+        for(int cj = 0; cj < NCH; cj++) {
+            if(angles) angles[ly.angle_off + (unsigned)cj * N + x] = acc[cj];
+            out[(unsigned)cj * N + x] = act_lc(acc[cj], l);
+        }
+    }
     template<int NCH>
-    __device__ __forceinline__ void layer_forward(const CnnLayerDev& ly, unsigned l, const cplx* __restrict__ wgt, bool staged,
-                                                  const cplx* in, cplx* out, cplx* angles) const {
+    __device__ __forceinline__ void site_outputs_nch(const CnnLayerDev& ly, unsigned l, const cplx* __restrict__ wgt, const cplx* in,
+                                                     const double* in_real, unsigned x, cplx* out, cplx* angles) const {
+        if(l == 0u) { site_outputs<NCH, 1, true>(ly, l, wgt, in, in_real, x, out, angles); return; }
+        if(NCH <= 4) {
+            switch(ly.prev) {
+                case 1: site_outputs<NCH, 1, false>(ly, l, wgt, in, in_real, x, out, angles); return;
+                case 2: site_outputs<NCH, 2, false>(ly, l, wgt, in, in_real, x, out, angles); return;
+                case 3: site_outputs<NCH, 3, false>(ly, l, wgt, in, in_real, x, out, angles); return;
+                case 4: site_outputs<NCH, 4, false>(ly, l, wgt, in, in_real, x, out, angles); return;
+                default: break;
+            }
+        }
+        site_outputs<NCH, 0, false>(ly, l, wgt, in, in_real, x, out, angles);
+    }
+    __device__ __forceinline__ void site_outputs_any(const CnnLayerDev& ly, unsigned l, const cplx* __restrict__ wgt, const cplx* in,
+                                                     const double* in_real, unsigned x, cplx* out, cplx* angles) const {
+        switch(ly.nch) {                 // compile-time channel count: no predicated-off FP64 work
+            case 1: site_outputs_nch<1>(ly, l, wgt, in, in_real, x, out, angles); break;
+            case 2: site_outputs_nch<2>(ly, l, wgt, in, in_real, x, out, angles); break;
+            case 3: site_outputs_nch<3>(ly, l, wgt, in, in_real, x, out, angles); break;
+            case 4: site_outputs_nch<4>(ly, l, wgt, in, in_real, x, out, angles); break;
+            case 5: site_outputs_nch<5>(ly, l, wgt, in, in_real, x, out, angles); break;
+            case 6: site_outputs_nch<6>(ly, l, wgt, in, in_real, x, out, angles); break;
+            case 7: site_outputs_nch<7>(ly, l, wgt, in, in_real, x, out, angles); break;
+            default: site_outputs_nch<8>(ly, l, wgt, in, in_real, x, out, angles); break;
+        }
+    }
+    // un-staged weights (P > 1024): indexed through link_begin
+    template<int NCH>
+    __device__ __forceinline__ void layer_forward_unstaged(const CnnLayerDev& ly, unsigned l, const cplx* __restrict__ wgt,
+                                                           const cplx* in, cplx* out, cplx* angles) const {
         const unsigned lane = threadIdx.x & 31u;
         for(unsigned x = lane; x < N; x += 32u) {
             const unsigned* nb = ly.nbr + x * ly.vol;
@@ -249,27 +322,13 @@ struct CnnDev {
             cplx acc[NCH];
             #pragma unroll
             for(int cj = 0; cj < NCH; cj++) acc[cj] = cplx(0.0, 0.0);
-            if(staged) {
-                // weights of this site's symmetry class, in consumption order (see stage())
-                const cplx* wq = wgt + ly.begin_params + (size_t)wo * ly.prev * NCH;
-                for(unsigned c = 0; c < ly.vol; c++) {
-                    const cplx* src = in + nb[c];
-                    for(unsigned ci = 0; ci < ly.prev; ci++) {
-                        const cplx sv = src[ci * N];
-                        #pragma unroll
-                        for(int cj = 0; cj < NCH; cj++) cfma(acc[cj], wq[cj], sv);
-                        wq += NCH;
-                    }
-                }
-            } else {
-                for(unsigned c = 0; c < ly.vol; c++) {
-                    const unsigned src_idx = nb[c];
-                    for(unsigned ci = 0; ci < ly.prev; ci++) {
-                        const cplx sv = in[ci * N + src_idx];
-                        const unsigned* lb = ly.link_begin + ci * NCH;
-                        #pragma unroll
-                        for(int cj = 0; cj < NCH; cj++) cfma(acc[cj], wgt[lb[cj] + wo + c], sv);
-                    }
+            for(unsigned c = 0; c < ly.vol; c++) {
+                const unsigned src_idx = nb[c];
+                for(unsigned ci = 0; ci < ly.prev; ci++) {
+                    const cplx sv = in[ci * N + src_idx];
+                    const unsigned* lb = ly.link_begin + ci * NCH;
+                    #pragma unroll
+                    for(int cj = 0; cj < NCH; cj++) cfma(acc[cj], wgt[lb[cj] + wo + c], sv);
                 }
             }
             #pragma unroll
@@ -291,15 +350,19 @@ struct CnnDev {
         cplx result(0.0, 0.0);
         for(unsigned l = 0; l < num_layers; l++) {
             const CnnLayerDev& ly = L[l];
-            switch(ly.nch) {                 // compile-time channel count: no predicated-off FP64 work
-                case 1: layer_forward<1>(ly, l, wgt, blk != nullptr, in, out, angles); break;
-                case 2: layer_forward<2>(ly, l, wgt, blk != nullptr, in, out, angles); break;
-                case 3: layer_forward<3>(ly, l, wgt, blk != nullptr, in, out, angles); break;
-                case 4: layer_forward<4>(ly, l, wgt, blk != nullptr, in, out, angles); break;
-                case 5: layer_forward<5>(ly, l, wgt, blk != nullptr, in, out, angles); break;
-                case 6: layer_forward<6>(ly, l, wgt, blk != nullptr, in, out, angles); break;
-                case 7: layer_forward<7>(ly, l, wgt, blk != nullptr, in, out, angles); break;
-                default: layer_forward<8>(ly, l, wgt, blk != nullptr, in, out, angles); break;
+            if(blk) {
+                for(unsigned x = lane; x < N; x += 32u) site_outputs_any(ly, l, wgt, in, nullptr, x, out, angles);
+            } else {
+                switch(ly.nch) {
+                    case 1: layer_forward_unstaged<1>(ly, l, wgt, in, out, angles); break;
+                    case 2: layer_forward_unstaged<2>(ly, l, wgt, in, out, angles); break;
+                    case 3: layer_forward_unstaged<3>(ly, l, wgt, in, out, angles); break;
+                    case 4: layer_forward_unstaged<4>(ly, l, wgt, in, out, angles); break;
+                    case 5: layer_forward_unstaged<5>(ly, l, wgt, in, out, angles); break;
+                    case 6: layer_forward_unstaged<6>(ly, l, wgt, in, out, angles); break;
+                    case 7: layer_forward_unstaged<7>(ly, l, wgt, in, out, angles); break;
+                    default: layer_forward_unstaged<8>(ly, l, wgt, in, out, angles); break;
+                }
             }
             __syncwarp();
             if(l + 1u < num_layers) {
