@@ -83,6 +83,99 @@ class PauliSum:
         from .api import Operator
         return Operator(self, gpu)
 
+    # ---- operator algebra: a native stand-in for the QuantumExpression `PauliExpression` the reference's Python layer
+    # and tests build operators with (source/operator/Operator.cpp:18-39 consumes only term.first.a/.b and term.second).
+    # Per site the masks encode I = (0,0), X = (1,0), Y = (0,1), Z = (1,1) (include/basis/PauliString.hpp:18-21).
+    def copy(self):
+        return PauliSum(self.num_sites, list(self.coeffs), list(self.a), list(self.b))
+
+    def simplified(self, tol=0.0):
+        """Merge equal strings, drop those with |coefficient| <= tol."""
+        acc = {}
+        for c, a, b in zip(self.coeffs, self.a, self.b):
+            acc[(a, b)] = acc.get((a, b), 0.0) + c
+        out = PauliSum(self.num_sites)
+        for (a, b), c in acc.items():
+            if abs(c) > tol:
+                out.coeffs.append(complex(c)); out.a.append(a); out.b.append(b)
+        return out
+
+    def __add__(self, other):
+        if isinstance(other, (int, float, complex)):
+            other = PauliSum(self.num_sites).add(other, {})
+        assert other.num_sites == self.num_sites
+        return PauliSum(self.num_sites, self.coeffs + other.coeffs, self.a + other.a, self.b + other.b).simplified()
+
+    __radd__ = __add__
+
+    def __neg__(self):
+        return PauliSum(self.num_sites, [-c for c in self.coeffs], list(self.a), list(self.b))
+
+    def __sub__(self, other):
+        return self + (-other if isinstance(other, PauliSum) else -complex(other))
+
+    def __rsub__(self, other):
+        return (-self) + other
+
+    @staticmethod
+    def _string_product(a1, b1, a2, b2):
+        """(phase, a, b) of the product P1 P2 of two Pauli strings (P1 acts after P2)."""
+        # per-site type code t = a + 2 b: 0 I, 1 X, 2 Y, 3 Z;  X Y = i Z, Y Z = i X, Z X = i Y (and -i reversed)
+        phase_pow = 0                    # accumulated power of i
+        x1, y1, z1 = a1 & ~b1, ~a1 & b1, a1 & b1
+        x2, y2, z2 = a2 & ~b2, ~a2 & b2, a2 & b2
+        plus = (x1 & y2) | (y1 & z2) | (z1 & x2)
+        minus = (y1 & x2) | (z1 & y2) | (x1 & z2)
+        phase_pow = (bin(plus).count("1") - bin(minus).count("1")) % 4
+        # result type per site: bitwise in the (x, z) symplectic picture: X-part = a ^ b ... with this encoding the
+        # flip mask is f = a ^ b and the sign mask is b; products XOR both
+        f = (a1 ^ b1) ^ (a2 ^ b2)
+        bb = b1 ^ b2
+        return 1j ** phase_pow, f ^ bb, bb
+
+    def __mul__(self, other):
+        if isinstance(other, (int, float, complex)):
+            return PauliSum(self.num_sites, [c * other for c in self.coeffs], list(self.a), list(self.b))
+        assert other.num_sites == self.num_sites
+        out = PauliSum(self.num_sites)
+        for c1, a1, b1 in zip(self.coeffs, self.a, self.b):
+            for c2, a2, b2 in zip(other.coeffs, other.a, other.b):
+                ph, a, b = self._string_product(a1, b1, a2, b2)
+                out.coeffs.append(c1 * c2 * ph); out.a.append(a); out.b.append(b)
+        return out.simplified()
+
+    def __rmul__(self, other):
+        return self * other
+
+    def dagger(self):
+        """Hermitian conjugate (Pauli strings are Hermitian: only the coefficients are conjugated)."""
+        return PauliSum(self.num_sites, [c.conjugate() for c in self.coeffs], list(self.a), list(self.b))
+
+    def roll(self, shift):
+        """Translate every string by `shift` sites on the ring of num_sites sites (QuantumExpression's .roll)."""
+        n, mask = self.num_sites, (1 << self.num_sites) - 1
+        shift %= n
+        rot = lambda m: ((m << shift) | (m >> (n - shift))) & mask if shift else m   # noqa: E731
+        return PauliSum(n, list(self.coeffs), [rot(a) for a in self.a], [rot(b) for b in self.b])
+
+    def commutator(self, other):
+        return self * other - other * self
+
+    def matrix(self):
+        """Dense 2^N x 2^N matrix with the reference's conventions: basis index = configuration bitmask (bit i <-> site i,
+        1 <-> spin up), M[s, s'] = sum_n c_n <s| P_n |s'> as used by E_loc(s) = sum_s' M[s, s'] psi(s') / psi(s)
+        (include/basis/PauliString.hpp:193-255, include/operator/Operator.hpp:38-121).  Small N only."""
+        n, dim = self.num_sites, 1 << self.num_sites
+        assert n <= 14
+        M = np.zeros((dim, dim), dtype=np.complex128)
+        s = np.arange(dim, dtype=np.int64)
+        for c, a, b in zip(self.coeffs, self.a, self.b):
+            ny = bin(~a & b & (dim - 1)).count("1")
+            neg = np.array([bin(int(v)).count("1") for v in (~s & b & (dim - 1))]) & 1
+            coeff = c * ((-1j) ** ny) * np.where(neg, -1.0, 1.0)
+            M[s, s ^ (a ^ b)] += coeff
+        return M
+
 
 def propagator(H, dt):
     """First-order time-step operator 1 - i dt H as a PauliSum (identity string a = b = 0): the kind of operator the
