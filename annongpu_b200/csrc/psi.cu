@@ -102,16 +102,17 @@ PsiRBM::PsiRBM(unsigned N_, unsigned M_, const cplx* W, cplx fw_, cplx lp_) {
 }
 void PsiRBM::upload() {
     dW.upload(hW);
-    std::vector<cplx> t((size_t)N * M);
-    for(unsigned i = 0; i < N; i++) for(unsigned j = 0; j < M; j++) t[(size_t)j * N + i] = hW[(size_t)i * M + j];
-    dWt.upload(t);
-    // rows padded to 32*K complex for the register-resident sampler (rbm_kernels.cuh: k_mc_rbm)
+    // rows padded to a multiple of 32*K (warp sampler) / 256 (block sampler) complex for the register-resident samplers
+    // (rbm_kernels.cuh); when M already is such a multiple (C2: 256) the samplers read W itself
+    Mpad = 0;
     if(M <= 2048u) {
-        const unsigned Mp = (M <= 512u) ? 32u * (M <= 32u ? 1u : M <= 64u ? 2u : M <= 128u ? 4u : M <= 256u ? 8u : 16u)
-                                        : (unsigned)MC_BLOCK_T * ((M + MC_BLOCK_T - 1) / MC_BLOCK_T);
-        std::vector<cplx> wp((size_t)N * Mp, cplx(0.0, 0.0));
-        for(unsigned i = 0; i < N; i++) for(unsigned j = 0; j < M; j++) wp[(size_t)i * Mp + j] = hW[(size_t)i * M + j];
-        dWpad.upload(wp);
+        Mpad = (M <= 512u) ? 32u * (M <= 32u ? 1u : M <= 64u ? 2u : M <= 128u ? 4u : M <= 256u ? 8u : 16u)
+                           : (unsigned)MC_BLOCK_T * ((M + MC_BLOCK_T - 1) / MC_BLOCK_T);
+        if(Mpad != M) {
+            std::vector<cplx> wp((size_t)N * Mpad, cplx(0.0, 0.0));
+            for(unsigned i = 0; i < N; i++) std::memcpy(&wp[(size_t)i * Mpad], &hW[(size_t)i * M], sizeof(cplx) * M);
+            dWpad.upload(wp);
+        }
     }
 }
 void PsiRBM::log_psi(SampleSet& S, bool es_weights) {
@@ -220,19 +221,19 @@ void PsiRBM::mc_sample(const McParams& mc, SampleSet& S, unsigned long long* acc
     if(M <= 512u) {
         S.angles.resize(S.ns * M);
         switch(rbm_sampler_K(M)) {
-            case 1: launch_mc_rbm_k<1>(d, dWpad.p, mc, S, acc_rej_dev); break;
-            case 2: launch_mc_rbm_k<2>(d, dWpad.p, mc, S, acc_rej_dev); break;
-            case 4: launch_mc_rbm_k<4>(d, dWpad.p, mc, S, acc_rej_dev); break;
-            case 8: launch_mc_rbm_k<8>(d, dWpad.p, mc, S, acc_rej_dev); break;
-            default: launch_mc_rbm_k<16>(d, dWpad.p, mc, S, acc_rej_dev); break;
+            case 1: launch_mc_rbm_k<1>(d, Wpad(), mc, S, acc_rej_dev); break;
+            case 2: launch_mc_rbm_k<2>(d, Wpad(), mc, S, acc_rej_dev); break;
+            case 4: launch_mc_rbm_k<4>(d, Wpad(), mc, S, acc_rej_dev); break;
+            case 8: launch_mc_rbm_k<8>(d, Wpad(), mc, S, acc_rej_dev); break;
+            default: launch_mc_rbm_k<16>(d, Wpad(), mc, S, acc_rej_dev); break;
         }
         S.has_angles = true;
     } else if(M <= 2048u) {
         S.angles.resize(S.ns * M);
         const unsigned K = (M + MC_BLOCK_T - 1) / MC_BLOCK_T;          // 3..8
         auto launch = [&](auto kr, auto kc) {
-            if(d.fw.im == 0.0) kr<<<mc.num_chains_local, MC_BLOCK_T, 0, stream()>>>(d, dWpad.p, mc, S.conf.p, S.log_psi.p, S.angles.p, acc_rej_dev);
-            else kc<<<mc.num_chains_local, MC_BLOCK_T, 0, stream()>>>(d, dWpad.p, mc, S.conf.p, S.log_psi.p, S.angles.p, acc_rej_dev);
+            if(d.fw.im == 0.0) kr<<<mc.num_chains_local, MC_BLOCK_T, 0, stream()>>>(d, Wpad(), mc, S.conf.p, S.log_psi.p, S.angles.p, acc_rej_dev);
+            else kc<<<mc.num_chains_local, MC_BLOCK_T, 0, stream()>>>(d, Wpad(), mc, S.conf.p, S.log_psi.p, S.angles.p, acc_rej_dev);
         };
         switch(K) {
             case 3: launch(k_mc_rbm_block<3, true>, k_mc_rbm_block<3, false>); break;

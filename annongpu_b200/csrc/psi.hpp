@@ -54,10 +54,12 @@ struct PsiRBM : Psi {
     unsigned M = 0;
     cplx fw{1.0, 0.0};
     std::vector<cplx> hW;
-    DevBuf<cplx> dW, dWt, dWpad;
+    DevBuf<cplx> dW, dWpad;
+    unsigned Mpad = 0;
+    const cplx* Wpad() const { return Mpad == M ? dW.p : dWpad.p; }
 
     PsiRBM(unsigned N_, unsigned M_, const cplx* W, cplx fw_, cplx lp_);
-    RbmDev dev() const { return RbmDev{N, M, words, P, lp, fw, dW.p, dWt.p}; }
+    RbmDev dev() const { return RbmDev{N, M, words, P, lp, fw, dW.p}; }
     void upload();
     Psi* clone() const override { return new PsiRBM(N, M, hW.data(), fw, lp); }
     void get_params(cplx* out) const override { std::memcpy(out, hW.data(), sizeof(cplx) * P); }

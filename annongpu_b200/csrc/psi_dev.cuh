@@ -25,7 +25,6 @@ struct RbmDev {
     unsigned N, M, words, P;
     cplx     lp, fw;
     const cplx* W;     // [N][M]
-    const cplx* Wt;    // [M][N]  (for the lane-per-flip-group local-energy kernel)
 
     __host__ __device__ unsigned payload_elems() const { return M; }
     __host__ __device__ unsigned block_scratch_bytes() const { return 0u; }

@@ -6,10 +6,11 @@
 //              the loop (the reference: >= 8 __syncthreads + an M-way shared-atomic reduce + a global atomic per
 //              proposal, include/ensembles/MonteCarlo.hpp:135-177, PsiRBM.hpp:92-157).
 //              Bound: FP64 pipe (~16*M DFMA per proposal) — see DESIGN.md; compulsory HBM traffic is ~0.
-//  k_eloc_rbm  one warp per sample, ONE LANE PER FLIP GROUP: each lane walks the M hidden units for its own s',
-//              reading theta_j as a shared-memory broadcast and W^T[j][site] coalesced across lanes, so a
-//              psi(s')/psi(s) evaluation needs no cross-lane reduction at all.  Groups whose coefficient is
-//              exactly zero on s (XX+YY on aligned spins) are compacted away first.
+//  k_mc_rbm_block  the same chain on one 256-thread block for 512 < M <= 2048 (one barrier per proposal).
+//  k_eloc_rbm  a team of 1..8 warps per sample, FOUR LANES PER FLIP GROUP: each quad walks the M hidden units for its
+//              own s', reading theta_j from the team's shared memory and W[site][j] as 64 contiguous bytes, and
+//              combines with two shuffles.  Groups whose coefficient is exactly zero on s (XX+YY on aligned
+//              spins) are compacted away first.
 //  k_rbm_T     the factorised log-derivative: O[s][i*M+j] = sigma_si * T[s][j], T = fw * th0(theta)
 //              (PsiRBM.hpp:161-176) — ns*M complex instead of ns*N*M.
 //  k_rbm_dense_O  materialises the dense rows only when a caller asks for O_k_samples / a dense S.
