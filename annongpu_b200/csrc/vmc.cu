@@ -890,8 +890,16 @@ static ColPartials col_reduce_partials(TDVP& t, const cplx* X, bool want_mean) {
         const size_t colblocks = (2 * (size_t)t.rbm_M + 127) / 128;
         size_t want_chunks = ((size_t)ctx().num_sms * 2 + colblocks - 1) / colblocks;
         want_chunks = std::min<size_t>(want_chunks, std::max<size_t>(1, ((size_t)64 << 20) / ((size_t)P * sizeof(cplx))));
-        if(want_mean) want_chunks = 64;
-        chunks = (unsigned)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(64, want_chunks), (ns + RBM_TS - 1) / RBM_TS));
+        size_t max_chunks = 64;
+        if(want_mean) {
+            // k_col_reduce_rbm<true> launches jb x ib blocks per chunk: enough chunks for ~4 blocks per SM (C1: one block per
+            // chunk -> 512 chunks instead of 64, 635 -> ~80 us), bounded by the partial-sum traffic (2 x chunks x P x 16 B <= 64 MB)
+            want_chunks = ((size_t)ctx().num_sms * 4 + (size_t)jb * ib - 1) / ((size_t)jb * ib);
+            want_chunks = std::min<size_t>(want_chunks, std::max<size_t>(1, ((size_t)32 << 20) / ((size_t)P * sizeof(cplx))));
+            want_chunks = std::max<size_t>(want_chunks, 1);
+            max_chunks = 4096;
+        }
+        chunks = (unsigned)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(max_chunks, want_chunks), (ns + RBM_TS - 1) / RBM_TS));
         chunk = ((ns + chunks - 1) / chunks + RBM_TS - 1) / RBM_TS * RBM_TS; chunks = (unsigned)((ns + chunk - 1) / chunk);
         t.chunk_buf.resize((size_t)2 * chunks * P);
         cplx* pm = want_mean ? t.chunk_buf.p : nullptr; cplx* px = t.chunk_buf.p + (size_t)chunks * P;
