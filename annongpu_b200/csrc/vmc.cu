@@ -977,8 +977,11 @@ static ColPartials col_reduce_partials(TDVP& t, const cplx* X, bool want_mean) {
         const unsigned jb = ceil_div(t.rbm_M, 128), ib = ceil_div(t.rbm_N, RBM_IT);
         // chunks of whole 32-sample tiles: enough blocks to fill the GPU twice, but the partial-sum traffic
         // (chunks * P * 16 B written and read back) is kept below ~64 MB and chunks <= 64
-        const size_t colblocks = (2 * (size_t)t.rbm_M + 127) / 128;
-        size_t want_chunks = ((size_t)ctx().num_sms * 2 + colblocks - 1) / colblocks;
+        const size_t colblocks = (2 * (size_t)t.rbm_M + 63) / 64;     // k_colreduce_dmma blocks per chunk
+        // measured: C2 (N = 64, 80-register variant) is best with ~2 blocks per SM, C5 (N = 200) with ~4
+        const char* env_cf = getenv("ANGPU_CHUNK_FACTOR");
+        const size_t cf = env_cf ? (size_t)atoi(env_cf) : (t.rbm_N <= 64u ? 2 : 4);
+        size_t want_chunks = ((size_t)ctx().num_sms * cf + colblocks - 1) / colblocks;
         want_chunks = std::min<size_t>(want_chunks, std::max<size_t>(1, ((size_t)64 << 20) / ((size_t)P * sizeof(cplx))));
         size_t max_chunks = 64;
         if(want_mean) {
@@ -996,7 +999,7 @@ static ColPartials col_reduce_partials(TDVP& t, const cplx* X, bool want_mean) {
         if(want_mean) k_col_reduce_rbm<true><<<dim3(jb, ib, chunks), 128, 0, stream()>>>(t.S.conf.p, t.T.p, t.S.weight.p, X, ns, t.rbm_N, t.rbm_M, t.words, chunk, pm, px);
         else if(use_dmma()) {
             const dim3 g128(ceil_div(2 * t.rbm_M, 128), chunks), g64(ceil_div(2 * t.rbm_M, 64), chunks);
-            if(t.rbm_N <= 64u) k_colreduce_dmma<1, 128><<<g128, CD_WARPS * 32, 0, stream()>>>(t.S.conf.p, t.T.p, t.S.weight.p, X, ns, t.rbm_N, t.rbm_M, t.words, chunk, px);
+            if(t.rbm_N <= 64u) k_colreduce_dmma<1, 64><<<g64, CD_WARPS * 32, 0, stream()>>>(t.S.conf.p, t.T.p, t.S.weight.p, X, ns, t.rbm_N, t.rbm_M, t.words, chunk, px);
             else if(t.rbm_N <= 128u) k_colreduce_dmma<2, 64><<<g64, CD_WARPS * 32, 0, stream()>>>(t.S.conf.p, t.T.p, t.S.weight.p, X, ns, t.rbm_N, t.rbm_M, t.words, chunk, px);
             else k_colreduce_dmma<4, 64><<<g64, CD_WARPS * 32, 0, stream()>>>(t.S.conf.p, t.T.p, t.S.weight.p, X, ns, t.rbm_N, t.rbm_M, t.words, chunk, px);
         }
