@@ -289,7 +289,7 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 }
 __device__ __forceinline__ double bit_sign(const uint64_t* cw, unsigned i) { return ((cw[i >> 6] >> (i & 63u)) & 1ull) ? 1.0 : -1.0; }
 
-constexpr int RD_WARPS = 8, RD_KC = 32, RD_CB = 128, RD_PAD = 8;      // 64 samples per block, 128 real columns per pass
+constexpr int RD_KC = 32, RD_CB = 128, RD_PAD = 8;                    // 8 samples per warp, 128 real columns per pass
 constexpr int RD_STRIDE = RD_CB + RD_PAD;
 constexpr int RD_STAGE_DOUBLES = RD_KC * RD_STRIDE;
 constexpr size_t RD_SMEM = 2 * RD_STAGE_DOUBLES * sizeof(double);       // double-buffered V tile (cp.async)
@@ -302,11 +302,12 @@ __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsr
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template<int N_> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
 
-__global__ void __launch_bounds__(RD_WARPS * 32) k_rowdot_dmma(const uint64_t* __restrict__ conf, const cplx* __restrict__ T,
+template<int RW>                                          // warps per block: 8 samples each
+__global__ void __launch_bounds__(RW * 32) k_rowdot_dmma(const uint64_t* __restrict__ conf, const cplx* __restrict__ T,
         const cplx* __restrict__ v, size_t ns, unsigned N, unsigned M, unsigned words, cplx* __restrict__ a_out) {
     extern __shared__ __align__(16) double rd_smem[];
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u, row = lane >> 2, kq = lane & 3u;
-    const size_t s = (size_t)blockIdx.x * (RD_WARPS * 8) + warp * 8u + row;          // this lane's sample (A row / C row)
+    const size_t s = (size_t)blockIdx.x * (RW * 8) + warp * 8u + row;          // this lane's sample (A row / C row)
     uint64_t cw[MAXW] = {0ull, 0ull, 0ull, 0ull};
     #pragma unroll
     for(unsigned w = 0; w < (unsigned)MAXW; w++) if(s < ns && w < words) cw[w] = conf[s * words + w];
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(RD_WARPS * 32) k_rowdot_dmma(const uint64_t* _
     auto issue = [&](unsigned q) {
         double* dst = rd_smem + (q & 1u) * RD_STAGE_DOUBLES;
         const unsigned cb = (q / nkc) * RD_CB, i0 = (q % nkc) * RD_KC;
-        for(unsigned e = threadIdx.x; e < RD_KC * (RD_CB / 2); e += RD_WARPS * 32) {
+        for(unsigned e = threadIdx.x; e < RD_KC * (RD_CB / 2); e += RW * 32) {
             const unsigned kk = e / (RD_CB / 2), c = (e % (RD_CB / 2)) * 2u;
             const bool ok = (i0 + kk < N) && (cb + c < ncol);
             cp_async16_zfill(dst + kk * RD_STRIDE + c, ok ? (const void*)(vr + (size_t)(i0 + kk) * ncol + cb + c) : (const void*)vr, ok);
@@ -1138,8 +1139,14 @@ void TDVP::rowdot(const cplx* v_dev) {
     if(!ns) return;
     if(factorised && use_dmma()) {
         static bool attr_set = false;
-        if(!attr_set) { ANGPU_CUDA(cudaFuncSetAttribute(k_rowdot_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RD_SMEM)); attr_set = true; }
-        k_rowdot_dmma<<<ceil_div(ns, RD_WARPS * 8), RD_WARPS * 32, RD_SMEM, stream()>>>(S.conf.p, T.p, v_dev, ns, rbm_N, rbm_M, words, row_a.p);
+        if(!attr_set) {
+            ANGPU_CUDA(cudaFuncSetAttribute(k_rowdot_dmma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RD_SMEM));
+            ANGPU_CUDA(cudaFuncSetAttribute(k_rowdot_dmma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RD_SMEM));
+            attr_set = true;
+        }
+        // 64 samples per block, or 32 when that would leave SMs without a block (C2: 8192 samples -> 256 blocks, not 128)
+        if(ns >= (size_t)ctx().num_sms * 2 * 64) k_rowdot_dmma<8><<<ceil_div(ns, 64), 256, RD_SMEM, stream()>>>(S.conf.p, T.p, v_dev, ns, rbm_N, rbm_M, words, row_a.p);
+        else k_rowdot_dmma<4><<<ceil_div(ns, 32), 128, RD_SMEM, stream()>>>(S.conf.p, T.p, v_dev, ns, rbm_N, rbm_M, words, row_a.p);
     }
     else if(factorised) k_rowdot_rbm<<<ceil_div(ns, RBM_ST), 256, 0, stream()>>>(S.conf.p, T.p, v_dev, ns, rbm_N, rbm_M, words, row_a.p);
     else k_rowdot_dense<<<(unsigned)ns, 256, 0, stream()>>>(O.p, v_dev, P, row_a.p);
