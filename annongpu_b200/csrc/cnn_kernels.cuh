@@ -32,6 +32,63 @@ __host__ __device__ inline size_t cnn_inc_slice_bytes(const CnnDev& psi, const C
 
 #ifdef __CUDACC__
 
+// Recompute in place, layer by layer, the outputs listed for entry `idx` (a flipped site for the sampler, a flip group for
+// E_loc), keeping the old values in `backup`; `spin` already holds the flipped configuration.  All lanes of the warp.
+__device__ __forceinline__ void cnn_cone_recompute(const CnnDev& psi, const CnnIncDev& inc, unsigned idx, const cplx* __restrict__ wgt,
+                                                   const double* spin, cplx* act, cplx* backup) {
+    const unsigned lane = threadIdx.x & 31u, N = psi.N;
+    unsigned boff = 0;
+    for(unsigned l = 0; l < psi.num_layers; l++) {
+        const CnnLayerDev& ly = psi.L[l];
+        const unsigned cnt = inc.aff_cnt[l][idx];
+        const unsigned* list = inc.aff[l] + (size_t)idx * inc.aff_max[l];
+        cplx* out = act + ly.angle_off;
+        const cplx* in = l ? act + psi.L[l - 1u].angle_off : nullptr;
+        for(unsigned k = lane; k < cnt; k += 32u) {
+            const unsigned x = list[k];
+            for(unsigned cj = 0; cj < ly.nch; cj++) backup[boff + cj * inc.aff_max[l] + k] = out[cj * N + x];
+            psi.site_outputs_any(ly, l, wgt, in, spin, x, out, nullptr);
+        }
+        boff += ly.nch * inc.aff_max[l];
+        __syncwarp();
+    }
+}
+__device__ __forceinline__ void cnn_cone_restore(const CnnDev& psi, const CnnIncDev& inc, unsigned idx, cplx* act, const cplx* backup) {
+    const unsigned lane = threadIdx.x & 31u, N = psi.N;
+    unsigned boff = 0;
+    for(unsigned l = 0; l < psi.num_layers; l++) {
+        const CnnLayerDev& ly = psi.L[l];
+        const unsigned cnt = inc.aff_cnt[l][idx];
+        const unsigned* list = inc.aff[l] + (size_t)idx * inc.aff_max[l];
+        cplx* out = act + ly.angle_off;
+        for(unsigned k = lane; k < cnt; k += 32u) {
+            const unsigned x = list[k];
+            for(unsigned cj = 0; cj < ly.nch; cj++) out[cj * N + x] = backup[boff + cj * inc.aff_max[l] + k];
+        }
+        boff += ly.nch * inc.aff_max[l];
+    }
+    __syncwarp();
+}
+// full forward pass into the resident activations (forward_pass, PsiCNN.hpp:99-160)
+__device__ __forceinline__ void cnn_full_forward(const CnnDev& psi, const cplx* __restrict__ wgt, const double* spin, cplx* act) {
+    const unsigned lane = threadIdx.x & 31u;
+    for(unsigned l = 0; l < psi.num_layers; l++) {
+        const CnnLayerDev& ly = psi.L[l];
+        const cplx* in = l ? act + psi.L[l - 1u].angle_off : nullptr;
+        for(unsigned x = lane; x < psi.N; x += 32u) psi.site_outputs_any(ly, l, wgt, in, spin, x, act + ly.angle_off, nullptr);
+        __syncwarp();
+    }
+}
+// log psi from the resident last-layer activations, summed in the order of CnnDev::forward
+__device__ __forceinline__ cplx cnn_log_psi_resident(const CnnDev& psi, const cplx* act) {
+    const unsigned lane = threadIdx.x & 31u;
+    const CnnLayerDev& last = psi.L[psi.num_layers - 1u];
+    const cplx* o = act + last.angle_off;
+    cplx r(0.0, 0.0);
+    for(unsigned idx = lane; idx < last.nch * psi.N; idx += 32u) r += o[idx];
+    return psi.lp + psi.final_factor * warp_sum(r);
+}
+
 __global__ void __launch_bounds__(128)
 k_mc_cnn_inc(const CnnDev psi, const CnnIncDev inc, const McParams mc, uint64_t* __restrict__ conf_out,
              cplx* __restrict__ log_psi_out, unsigned long long* __restrict__ acc_rej) {
@@ -45,7 +102,7 @@ k_mc_cnn_inc(const CnnDev psi, const CnnIncDev inc, const McParams mc, uint64_t*
     double* spin = reinterpret_cast<double*>(backup + inc.backup_elems);       // the configuration as +-1.0 (layer-0 input)
     const unsigned chain = blockIdx.x * wpb + warp;
     if(chain >= mc.num_chains_local) return;
-    const unsigned gchain = mc.chain0 + chain, N = psi.N, NL = psi.num_layers;
+    const unsigned gchain = mc.chain0 + chain, N = psi.N;
     const unsigned tag_init = (mc.call << 1) | 0u, tag_step = (mc.call << 1) | 1u;
 
     uint32_t r4[4];
@@ -60,20 +117,8 @@ k_mc_cnn_inc(const CnnDev psi, const CnnIncDev inc, const McParams mc, uint64_t*
     }
     for(unsigned x = lane; x < N; x += 32u) spin[x] = conf_spin(conf, x);
     __syncwarp();
-    // full forward pass (forward_pass, PsiCNN.hpp:99-160)
-    for(unsigned l = 0; l < NL; l++) {
-        const CnnLayerDev& ly = psi.L[l];
-        const cplx* in = l ? act + psi.L[l - 1u].angle_off : nullptr;
-        for(unsigned x = lane; x < N; x += 32u) psi.site_outputs_any(ly, l, wgt, in, spin, x, act + ly.angle_off, nullptr);
-        __syncwarp();
-    }
-    const CnnLayerDev& last = psi.L[NL - 1u];
-    auto log_psi_now = [&]() -> cplx {
-        cplx r(0.0, 0.0);
-        const cplx* o = act + last.angle_off;
-        for(unsigned idx = lane; idx < last.nch * N; idx += 32u) r += o[idx];
-        return psi.lp + psi.final_factor * warp_sum(r);
-    };
+    cnn_full_forward(psi, wgt, spin, act);
+    auto log_psi_now = [&]() -> cplx { return cnn_log_psi_resident(psi, act); };
     cplx cur = log_psi_now();
 
     const unsigned therm = mc.num_therm * N, per_sample = mc.num_sweeps * N;
@@ -91,22 +136,7 @@ k_mc_cnn_inc(const CnnDev psi, const CnnIncDev inc, const McParams mc, uint64_t*
             conf_flip(conf, site);
             if(lane == 0) spin[site] = -spin[site];
             __syncwarp();
-            // recompute the receptive cone of `site` in place, layer by layer, keeping the old values
-            unsigned boff = 0;
-            for(unsigned l = 0; l < NL; l++) {
-                const CnnLayerDev& ly = psi.L[l];
-                const unsigned cnt = inc.aff_cnt[l][site];
-                const unsigned* list = inc.aff[l] + (size_t)site * inc.aff_max[l];
-                cplx* out = act + ly.angle_off;
-                const cplx* in = l ? act + psi.L[l - 1u].angle_off : nullptr;
-                for(unsigned k = lane; k < cnt; k += 32u) {
-                    const unsigned x = list[k];
-                    for(unsigned cj = 0; cj < ly.nch; cj++) backup[boff + cj * inc.aff_max[l] + k] = out[cj * N + x];
-                    psi.site_outputs_any(ly, l, wgt, in, spin, x, out, nullptr);
-                }
-                boff += ly.nch * inc.aff_max[l];
-                __syncwarp();
-            }
+            cnn_cone_recompute(psi, inc, site, wgt, spin, act, backup);      // the receptive cone of `site`, old values kept
             const cplx nlp = log_psi_now();
             if(metropolis_accept(2.0 * (nlp.re - cur.re), u)) {
                 cur = nlp;
@@ -114,19 +144,7 @@ k_mc_cnn_inc(const CnnDev psi, const CnnIncDev inc, const McParams mc, uint64_t*
             } else {
                 conf_flip(conf, site);
                 if(lane == 0) spin[site] = -spin[site];
-                boff = 0;
-                for(unsigned l = 0; l < NL; l++) {
-                    const CnnLayerDev& ly = psi.L[l];
-                    const unsigned cnt = inc.aff_cnt[l][site];
-                    const unsigned* list = inc.aff[l] + (size_t)site * inc.aff_max[l];
-                    cplx* out = act + ly.angle_off;
-                    for(unsigned k = lane; k < cnt; k += 32u) {
-                        const unsigned x = list[k];
-                        for(unsigned cj = 0; cj < ly.nch; cj++) out[cj * N + x] = backup[boff + cj * inc.aff_max[l] + k];
-                    }
-                    boff += ly.nch * inc.aff_max[l];
-                }
-                __syncwarp();
+                cnn_cone_restore(psi, inc, site, act, backup);
             }
             if(t0 + b + 1u == next_record) {
                 if(lane == 0) {
@@ -140,6 +158,61 @@ k_mc_cnn_inc(const CnnDev psi, const CnnIncDev inc, const McParams mc, uint64_t*
         }
     }
     if(lane == 0) { atomicAdd(&acc_rej[0], acc); atomicAdd(&acc_rej[1], total_steps - acc); }
+}
+
+// E_loc for PsiCNN with the same machinery: one warp per sample keeps the activations of s resident, and every active
+// flip group re-evaluates only the union of the receptive cones of its flipped sites (lists per group precomputed on the
+// host, `inc` indexed by group), restoring afterwards.  psi(s')/psi(s) is bit-identical to two full forward passes
+// (Operator.hpp:38-121 with PsiCNN.hpp:164-175).
+__global__ void __launch_bounds__(128)
+k_eloc_cnn_inc(const CnnDev psi, const CnnIncDev inc, const OpDev op, const uint64_t* __restrict__ confs, size_t ns,
+               cplx* __restrict__ eloc_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const unsigned lane = threadIdx.x & 31u, wpb = blockDim.x >> 5, warp = threadIdx.x >> 5;
+    const size_t slice = cnn_inc_slice_bytes(psi, inc);
+    const cplx* __restrict__ wgt = reinterpret_cast<const cplx*>(psi.stage(smem_raw + (size_t)wpb * slice));
+    cplx* act = reinterpret_cast<cplx*>(smem_raw + (size_t)warp * slice);
+    cplx* backup = act + psi.num_angles;
+    double* spin = reinterpret_cast<double*>(backup + inc.backup_elems);
+    const unsigned N = psi.N, G = op.num_groups;
+    for(size_t s = (size_t)blockIdx.x * wpb + warp; s < ns; s += (size_t)gridDim.x * wpb) {
+        uint64_t conf[MAXW];
+        conf_load(conf, confs + s * psi.words, psi.words);
+        for(unsigned x = lane; x < N; x += 32u) spin[x] = conf_spin(conf, x);
+        __syncwarp();
+        cnn_full_forward(psi, wgt, spin, act);
+        const cplx lp = cnn_log_psi_resident(psi, act);
+        cplx E(0.0, 0.0);
+        for(unsigned n = lane; n < op.num_diag; n += 32u) E += string_sign_reg(op, n, conf) * op.coef[n];
+        E = warp_sum(E);
+        for(unsigned g0 = 0; g0 < G; g0 += 32u) {
+            const unsigned gl = g0 + lane;
+            cplx C(0.0, 0.0);
+            if(gl < G) C = strings_coefficient_reg(op, op.group_begin[gl], op.group_begin[gl + 1u], conf);
+            unsigned active = __ballot_sync(FULL, C.re != 0.0 || C.im != 0.0);
+            while(active) {                                      // warp-uniform loop over the active groups of this batch
+                const unsigned src = (unsigned)__ffs((int)active) - 1u, g = g0 + src;
+                active &= active - 1u;
+                const cplx Cg(__shfl_sync(FULL, C.re, src), __shfl_sync(FULL, C.im, src));
+                // flip the group's sites in the +-1 copy (lane w handles word w of the mask)
+                if(lane < op.words) {
+                    uint64_t m = op.flip[g * op.words + lane];
+                    while(m) { const unsigned p = lane * 64u + (unsigned)__ffsll((long long)m) - 1u; spin[p] = -spin[p]; m &= m - 1ull; }
+                }
+                __syncwarp();
+                cnn_cone_recompute(psi, inc, g, wgt, spin, act, backup);
+                const cplx lp2 = cnn_log_psi_resident(psi, act);
+                E += Cg * cexp(lp2 - lp);
+                if(lane < op.words) {
+                    uint64_t m = op.flip[g * op.words + lane];
+                    while(m) { const unsigned p = lane * 64u + (unsigned)__ffsll((long long)m) - 1u; spin[p] = -spin[p]; m &= m - 1ull; }
+                }
+                cnn_cone_restore(psi, inc, g, act, backup);
+            }
+        }
+        if(lane == 0) eloc_out[s] = E;
+        __syncwarp();
+    }
 }
 
 #endif // __CUDACC__

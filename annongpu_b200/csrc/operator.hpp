@@ -32,6 +32,7 @@ struct Operator {
     unsigned num_strings = 0, words = 1;
     // caller's original order (kept for copies / introspection)
     std::vector<cplx> h_coef; std::vector<uint64_t> h_a, h_b;
+    std::vector<uint64_t> h_flip;          // [num_groups][words]: the flip mask of every off-diagonal group (device order)
     DevBuf<cplx> d_coef; DevBuf<uint64_t> d_b, d_flip; DevBuf<unsigned> d_group_begin;
     OpDev dev{};
 
@@ -75,6 +76,7 @@ struct Operator {
             ng++;
         }
         begin.push_back((unsigned)coef.size());
+        h_flip = flip;
         d_coef.upload(coef); d_b.upload(bmask); d_flip.upload(flip); d_group_begin.upload(begin);
         dev = OpDev{num_strings, num_diag, ng, words, max_flips, d_coef.p, d_b.p, d_flip.p, d_group_begin.p};
     }

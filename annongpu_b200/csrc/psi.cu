@@ -442,7 +442,9 @@ void PsiCNN::build() {
     d_sym.upload(sym); d_params.upload(params);
     // receptive cones for the incremental sampler: affected_0(p) = {x : p in nbr_0(x, .)}, affected_l = preimage of affected_{l-1}
     d_aff.clear(); d_aff_cnt.clear(); d_aff.resize(num_layers); d_aff_cnt.resize(num_layers);
-    std::vector<std::vector<std::vector<unsigned>>> cone(num_layers, std::vector<std::vector<unsigned>>(N));
+    h_cone.assign(num_layers, std::vector<std::vector<unsigned>>(N));
+    auto& cone = h_cone;
+    gaff_hash = 0; gaff_groups = 0; d_gaff.clear();
     for(unsigned l = 0; l < num_layers; l++) {
         const unsigned vol = layer_dev[l].vol;
         aff_max[l] = 0;
@@ -471,7 +473,63 @@ CnnDev PsiCNN::dev(bool keep_angles) const {
 }
 // only O_k (back-propagation) needs the recorded pre-activations: the other kernels run with the smaller per-warp scratch
 void PsiCNN::log_psi(SampleSet& S, bool es_weights) { generic_log_psi(dev(false), S, es_weights); }
-void PsiCNN::eloc(const Operator& op, SampleSet& S) { generic_eloc(dev(false), op, S); }
+void PsiCNN::eloc(const Operator& op, SampleSet& S) {
+    if(S.ns == 0) return;
+    const CnnDev d = dev(false);
+    const size_t bb = d.block_scratch_bytes();
+    const char* env = getenv("ANGPU_CNN_ELOC");                // "generic" forces one full forward per flip group
+    if((env && std::string(env) == "generic") || bb == 0 || op.dev.num_groups == 0) { generic_eloc(d, op, S); return; }
+    ANGPU_REQUIRE(op.words == words, "operator / wavefunction word count mismatch");
+    // union of the receptive cones of every flip group's sites, per layer (cached per operator)
+    const unsigned G = op.dev.num_groups;
+    uint64_t key = 1469598103934665603ull;                      // FNV-1a over the flip masks: the cache is keyed by content
+    for(uint64_t m : op.h_flip) { key ^= m; key *= 1099511628211ull; }
+    key ^= G; key *= 1099511628211ull;
+    if(gaff_hash != key || gaff_groups != G || d_gaff.size() != num_layers) {
+        d_gaff.clear(); d_gaff_cnt.clear(); d_gaff.resize(num_layers); d_gaff_cnt.resize(num_layers);
+        for(unsigned l = 0; l < num_layers; l++) {
+            std::vector<std::vector<unsigned>> uni(G);
+            gaff_max[l] = 0;
+            for(unsigned g = 0; g < G; g++) {
+                std::set<unsigned> u;
+                for(unsigned w = 0; w < words; w++) {
+                    uint64_t m = op.h_flip[(size_t)g * words + w];
+                    while(m) {
+                        const unsigned p = w * 64u + (unsigned)__builtin_ctzll(m);
+                        ANGPU_REQUIRE(p < N, "operator acts on a site beyond the lattice");
+                        u.insert(h_cone[l][p].begin(), h_cone[l][p].end());
+                        m &= m - 1ull;
+                    }
+                }
+                uni[g].assign(u.begin(), u.end());
+                gaff_max[l] = std::max<unsigned>(gaff_max[l], (unsigned)u.size());
+            }
+            std::vector<unsigned> flat((size_t)G * gaff_max[l], 0u), cnt(G);
+            for(unsigned g = 0; g < G; g++) { cnt[g] = (unsigned)uni[g].size(); std::copy(uni[g].begin(), uni[g].end(), flat.begin() + (size_t)g * gaff_max[l]); }
+            d_gaff[l].upload(flat); d_gaff_cnt[l].upload(cnt);
+        }
+        gaff_hash = key; gaff_groups = G;
+    }
+    CnnIncDev inc{};
+    inc.backup_elems = 0;
+    for(unsigned l = 0; l < num_layers; l++) {
+        inc.aff[l] = d_gaff[l].p; inc.aff_cnt[l] = d_gaff_cnt[l].p; inc.aff_max[l] = gaff_max[l];
+        inc.backup_elems += layer_dev[l].nch * gaff_max[l];
+    }
+    const size_t slice = cnn_inc_slice_bytes(d, inc), cap = ctx().smem_optin;
+    if(slice + bb > cap) { generic_eloc(d, op, S); return; }
+    unsigned wpb = 1, best = 0;
+    for(unsigned w = 1; w <= 4; w++) {
+        if(w * slice + bb > cap) break;
+        const unsigned resident = w * (unsigned)std::min<size_t>(32, (size_t)(228 * 1024) / (w * slice + bb + 1024));
+        if(resident >= best) { best = resident; wpb = w; }
+    }
+    const size_t smem = wpb * slice + bb;
+    const unsigned grid = (unsigned)std::min<size_t>((S.ns + wpb - 1) / wpb, (size_t)ctx().num_sms * 32);
+    set_smem(k_eloc_cnn_inc, smem);
+    k_eloc_cnn_inc<<<grid, wpb * 32, smem, stream()>>>(d, inc, op.dev, S.conf.p, S.ns, S.eloc.p);
+    ANGPU_CHECK_LAUNCH(); count_launch();
+}
 void PsiCNN::ok_rows(SampleSet& S, size_t s0, size_t cnt, cplx* out) { generic_ok(dev(true), S, s0, cnt, out); }
 void PsiCNN::mc_sample(const McParams& mc, SampleSet& S, unsigned long long* a) {
     const CnnDev d = dev(false);

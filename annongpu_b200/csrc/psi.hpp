@@ -118,6 +118,11 @@ struct PsiCNN : Psi {
     // incremental sampler (cnn_kernels.cuh): per layer and flipped site, the output sites inside the receptive cone
     std::vector<DevBuf<unsigned>> d_aff, d_aff_cnt;
     unsigned aff_max[CNN_MAX_LAYERS] = {0, 0, 0, 0};
+    std::vector<std::vector<std::vector<unsigned>>> h_cone;     // [layer][site] -> sorted affected output sites
+    // per-operator union cones of the flip groups (cone-based E_loc), cached for the last operator seen
+    std::vector<DevBuf<unsigned>> d_gaff, d_gaff_cnt;
+    unsigned gaff_max[CNN_MAX_LAYERS] = {0, 0, 0, 0};
+    uint64_t gaff_hash = 0; unsigned gaff_groups = 0;
 
     PsiCNN(const unsigned* extent_, unsigned num_layers_, const unsigned* num_channels_, const unsigned* connectivity_,
            const unsigned* symmetry_classes, const cplx* params_, unsigned num_params, double final_factor_, cplx lp_);

@@ -523,3 +523,30 @@ def test_json_round_trip(gpu, name):
     assert np.array_equal(psi2.params, psi.params) and psi2.log_prefactor == psi.log_prefactor
     es = gpu.ExactSummationSpins(N)
     assert np.array_equal(gpu.log_psi_vector(psi2, es), gpu.log_psi_vector(psi, es))
+
+
+@pytest.mark.parametrize("name", ["cnn", "cnn_sym", "C3"])
+def test_cnn_cone_local_energy_bit_identical_to_full_forward(gpu, name):
+    """The cone-based PsiCNN E_loc (only the union of the receptive cones of a flip group is recomputed) against the
+    generic kernel (one full forward pass per flip group): identical local energies, for two different operators in a row
+    (the per-operator cone lists are cached by content)."""
+    import os
+    if name == "C3":
+        spec, H = F.config_C3()
+        N = 100
+    else:
+        spec, H, N = zoo()[name]
+    H2 = F.tfim(N, F.ring_bonds(N), h=0.7)
+    psi = make_psi(gpu, spec)
+    rng = np.random.default_rng(5)
+    confs = _sample_confs(rng, N, 40)
+    out = {}
+    try:
+        for mode in ("cone", "generic"):
+            os.environ["ANGPU_CNN_ELOC"] = mode
+            out[mode] = [gpu.local_energies(psi, make_op(gpu, h), confs)[1] for h in (H, H2, H)]
+    finally:
+        os.environ["ANGPU_CNN_ELOC"] = "cone"
+    for a, b in zip(out["cone"], out["generic"]):
+        assert rel_err(a, b) <= 1e-13
+    assert np.array_equal(out["cone"][0], out["cone"][2])
