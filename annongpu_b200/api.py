@@ -205,6 +205,8 @@ class Operator:
         """Same operator with masks padded to `words` 64-bit words (to match a wider wavefunction)."""
         if words == self.words:
             return self
+        if words < self.words and any(int(m) >> (64 * words) for m in list(self.a_masks) + list(self.b_masks)):
+            raise RuntimeError(f"operator acts on sites beyond {64 * words}: it does not fit a wavefunction of {words} mask word(s)")
         return Operator(None, True, _raw=(self.coefficients, self.a_masks, self.b_masks, 64 * words))
 
     @property

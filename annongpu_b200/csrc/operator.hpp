@@ -33,6 +33,7 @@ struct Operator {
     // caller's original order (kept for copies / introspection)
     std::vector<cplx> h_coef; std::vector<uint64_t> h_a, h_b;
     std::vector<uint64_t> h_flip;          // [num_groups][words]: the flip mask of every off-diagonal group (device order)
+    unsigned num_sites_touched = 0;        // 1 + the highest site any string acts on (0 for a pure identity)
     DevBuf<cplx> d_coef; DevBuf<uint64_t> d_b, d_flip; DevBuf<unsigned> d_group_begin;
     OpDev dev{};
 
@@ -77,10 +78,22 @@ struct Operator {
         }
         begin.push_back((unsigned)coef.size());
         h_flip = flip;
+        num_sites_touched = 0;
+        for(unsigned i = 0; i < num_strings; i++)
+            for(unsigned w = 0; w < words; w++) {
+                const uint64_t m = h_a[i * words + w] | h_b[i * words + w];
+                if(m) num_sites_touched = std::max(num_sites_touched, w * 64u + 64u - (unsigned)__builtin_clzll(m));
+            }
         d_coef.upload(coef); d_b.upload(bmask); d_flip.upload(flip); d_group_begin.upload(begin);
         dev = OpDev{num_strings, num_diag, ng, words, max_flips, d_coef.p, d_b.p, d_flip.p, d_group_begin.p};
     }
 };
+
+// every kernel indexes the wavefunction by the sites an operator touches: reject operators wider than the state
+inline void require_operator_fits(const Operator& op, unsigned num_sites, unsigned words) {
+    ANGPU_REQUIRE(op.words == words, "operator / wavefunction word count mismatch");
+    ANGPU_REQUIRE(op.num_sites_touched <= num_sites, "operator acts on site " + std::to_string(op.num_sites_touched - 1) + " but the wavefunction has " + std::to_string(num_sites) + " sites");
+}
 
 #ifdef __CUDACC__
 // sign (-1)^{popc(~s & b)} of string n on configuration s (uniform over the warp)

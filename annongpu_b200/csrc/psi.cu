@@ -149,8 +149,8 @@ static void launch_eloc_rbm(const RbmDev& d, const Operator& op, SampleSet& S) {
     ANGPU_CHECK_LAUNCH(); count_launch();
 }
 void PsiRBM::eloc(const Operator& op, SampleSet& S) {
+    require_operator_fits(op, N, words);
     if(S.ns == 0) return;
-    ANGPU_REQUIRE(op.words == words, "operator / wavefunction word count mismatch");
     const size_t budget = std::min<size_t>(ctx().smem_optin, 200 * 1024);
     if(op.dev.max_flips > (unsigned)RBM_ELOC_MAXF || rbm_eloc_slice_bytes(M, op.dev.num_groups, RBM_ELOC_WARPS) > budget) { generic_eloc(dev(), op, S); return; }
     ensure_angles(S);
@@ -375,7 +375,7 @@ void PsiDeep::set_params(const cplx* in) {
     upload();
 }
 void PsiDeep::log_psi(SampleSet& S, bool es_weights) { generic_log_psi(dev(), S, es_weights); }
-void PsiDeep::eloc(const Operator& op, SampleSet& S) { generic_eloc(dev(), op, S); }
+void PsiDeep::eloc(const Operator& op, SampleSet& S) { require_operator_fits(op, N, words); generic_eloc(dev(), op, S); }
 void PsiDeep::ok_rows(SampleSet& S, size_t s0, size_t cnt, cplx* out) { generic_ok(dev(), S, s0, cnt, out); }
 void PsiDeep::mc_sample(const McParams& mc, SampleSet& S, unsigned long long* a) {
     const char* env_s = getenv("ANGPU_DEEP_SAMPLER");          // "generic" forces the warp-per-chain kernel (tests, A/B timing)
@@ -474,6 +474,7 @@ CnnDev PsiCNN::dev(bool keep_angles) const {
 // only O_k (back-propagation) needs the recorded pre-activations: the other kernels run with the smaller per-warp scratch
 void PsiCNN::log_psi(SampleSet& S, bool es_weights) { generic_log_psi(dev(false), S, es_weights); }
 void PsiCNN::eloc(const Operator& op, SampleSet& S) {
+    require_operator_fits(op, N, words);
     if(S.ns == 0) return;
     const CnnDev d = dev(false);
     const size_t bb = d.block_scratch_bytes();
@@ -565,7 +566,7 @@ PsiClassical::PsiClassical(unsigned num_sites, unsigned order_, unsigned num_ops
     ANGPU_REQUIRE(order == 1u || order == 2u, "PsiClassical: order must be 1 or 2");
     ANGPU_REQUIRE(num_own == num_ops, "PsiClassical: one parameter per local operator");
     for(unsigned i = 0; i < num_ops; i++) {
-        ANGPU_REQUIRE(ops_[i]->words == words, "PsiClassical: operator word count mismatch");
+        require_operator_fits(*ops_[i], N, words);
         ops.emplace_back(new Operator(*ops_[i]));
     }
     own_params.assign(params_, params_ + num_own);
@@ -601,7 +602,7 @@ void PsiClassical::set_params(const cplx* in) {
     if(order > 1u && ref) ref->set_params(in + own_params.size());
 }
 void PsiClassical::log_psi(SampleSet& S, bool es_weights) { generic_log_psi(dev(), S, es_weights); }
-void PsiClassical::eloc(const Operator& op, SampleSet& S) { generic_eloc(dev(), op, S); }
+void PsiClassical::eloc(const Operator& op, SampleSet& S) { require_operator_fits(op, N, words); generic_eloc(dev(), op, S); }
 void PsiClassical::ok_rows(SampleSet& S, size_t s0, size_t cnt, cplx* out) { generic_ok(dev(), S, s0, cnt, out); }
 void PsiClassical::mc_sample(const McParams& mc, SampleSet& S, unsigned long long* a) { generic_mc(dev(), mc, S, a); }
 

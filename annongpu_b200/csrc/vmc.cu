@@ -935,7 +935,7 @@ __global__ void k_exp_fast_energy(const OpDev op, const uint64_t* __restrict__ c
     }
 }
 cplx ExpectationValue::exp_sigma_z(const Operator& op, Psi& psi, Ensemble& ens) {
-    ANGPU_REQUIRE(op.words == psi.words, "operator / wavefunction word count mismatch");
+    require_operator_fits(op, psi.N, psi.words);
     ens.generate(psi, S);
     if(S.ns) {
         k_exp_fast_energy<<<grid_for(S.ns * 32), 256, 0, stream()>>>(op.dev, S.conf.p, S.ns, S.eloc.p);
