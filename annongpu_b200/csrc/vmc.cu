@@ -170,12 +170,15 @@ __global__ void __launch_bounds__(128) k_col_reduce_rbm(const uint64_t* __restri
 }
 
 // out[k] = sum_ch part[ch][k]  (fixed order)
-__global__ void k_sum_chunks(const cplx* __restrict__ part, unsigned chunks, size_t P, cplx* __restrict__ out) {
+__global__ void k_sum_chunks(const cplx* __restrict__ part, unsigned chunks, size_t P, cplx* __restrict__ out, bool conj_out = false) {
     for(size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < P; k += (size_t)gridDim.x * blockDim.x) {
         cplx a(0.0, 0.0);
         for(unsigned c = 0; c < chunks; c++) a += part[(size_t)c * P + k];
-        out[k] = a;
+        out[k] = conj_out ? conj(a) : a;
     }
+}
+__global__ void k_fill_cplx(cplx* p, cplx v, size_t n) {
+    for(size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) p[k] = v;
 }
 
 // a_s = O_s . v   (dense rows; one block per sample)
@@ -1018,6 +1021,21 @@ static ColPartials col_reduce_partials(TDVP& t, const cplx* X, bool want_mean) {
 }
 // mean_out / x_out: [P] device; X: per-sample complex factor
 static void col_reduce(TDVP& t, const cplx* X, cplx* mean_out, cplx* x_out) {
+    // factorised rows with enough sites to fill the 8-row MMA tiles: both sums on the FP64 tensor cores, as two passes of
+    // the same kernel (x with the given X; the mean as conj(sum_s w_s conj(O_sk)), i.e. X = 1)
+    if(mean_out && t.factorised && use_dmma() && t.rbm_N >= 32u && t.S.ns >= 1024) {
+        const ColPartials cx = col_reduce_partials(t, X, false);
+        k_sum_chunks<<<grid_for(t.P), 256, 0, stream()>>>(cx.x, cx.chunks, t.P, x_out);
+        if(t.ones.n < t.S.ns) {
+            t.ones.resize(t.S.ns);
+            k_fill_cplx<<<grid_for(t.S.ns), 256, 0, stream()>>>(t.ones.p, cplx(1.0, 0.0), t.S.ns);
+            count_launch();
+        }
+        const ColPartials cm = col_reduce_partials(t, t.ones.p, false);
+        k_sum_chunks<<<grid_for(t.P), 256, 0, stream()>>>(cm.x, cm.chunks, t.P, mean_out, true);
+        ANGPU_CHECK_LAUNCH(); count_launch(2);
+        return;
+    }
     const ColPartials cp = col_reduce_partials(t, X, mean_out != nullptr);
     if(mean_out) { k_sum_chunks<<<grid_for(t.P), 256, 0, stream()>>>(cp.mean, cp.chunks, t.P, mean_out); ANGPU_CHECK_LAUNCH(); count_launch(); }
     k_sum_chunks<<<grid_for(t.P), 256, 0, stream()>>>(cp.x, cp.chunks, t.P, x_out);

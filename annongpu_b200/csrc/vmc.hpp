@@ -74,7 +74,7 @@ struct TDVP {
     DevBuf<cplx> Smat;                       // P x P row-major, S = <O_k* O_k'> - <O_k>*<O_k'>
     DevBuf<cplx> O;                          // dense O_k_samples [ns][P] (valid iff have_dense_O)
     DevBuf<cplx> T;                          // PsiRBM factorised form [ns][M] (valid iff factorised)
-    DevBuf<cplx> chunk_buf, row_a, vec_in, vec_out, cg_buf, vb_part;
+    DevBuf<cplx> chunk_buf, row_a, vec_in, vec_out, cg_buf, vb_part, ones;
     DevBuf<double> d_scal;
     bool have_dense_O = false, factorised = false, have_S = false, evaluated = false;
     unsigned rbm_N = 0, rbm_M = 0, words = 1;
