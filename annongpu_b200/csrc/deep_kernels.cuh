@@ -143,6 +143,126 @@ k_mc_deep_block(const DeepDev psi, const cplx* __restrict__ w1d, const McParams 
     if(j == 0 && valid) { atomicAdd(&acc_rej[0], acc); atomicAdd(&acc_rej[1], total_steps - acc); }
 }
 
+// E_loc for PsiDeep with the same register-resident deep layers: ONE BLOCK PER SAMPLE, the 4 thread groups evaluate 4
+// active flip groups per round (psi(s')/psi(s) for 4 different s' at once), three barriers per round.
+// (Operator.hpp:38-121 with PsiDeep.hpp:219-343.)  Dynamic shared memory: list_C[G] cplx | list_g[G] unsigned.
+template<int NDEEP>
+__global__ void __launch_bounds__(DEEP_BLK_T, NDEEP == 1 ? 2 : 1)
+k_eloc_deep_block(const DeepDev psi, const cplx* __restrict__ w1d, const OpDev op, const uint64_t* __restrict__ confs, size_t ns,
+                  cplx* __restrict__ eloc_out) {
+    extern __shared__ __align__(16) unsigned char deep_dyn[];
+    __shared__ cplx actv[DEEP_BLK_NC][DEEP_BLK_W];
+    __shared__ cplx part[DEEP_BLK_NC][DEEP_BLK_NC][DEEP_BLK_W];
+    __shared__ cplx fin[DEEP_BLK_NC][2];
+    __shared__ cplx esum[DEEP_BLK_T / 32];
+    __shared__ unsigned count_sh;
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, j = tid & (DEEP_BLK_W - 1), ib = tid / DEEP_BLK_W;
+    const unsigned c = ib, N = psi.N, S1 = psi.L[1].size, G = op.num_groups;
+    cplx* list_C = reinterpret_cast<cplx*>(deep_dyn);
+    unsigned* list_g = reinterpret_cast<unsigned*>(list_C + G);
+
+    cplx wreg[NDEEP][DEEP_BLK_R], bias[NDEEP], fw(0.0, 0.0);
+    #pragma unroll
+    for(int d = 0; d < NDEEP; d++) {
+        const DeepLayerDev& ly = psi.L[2 + d];
+        const cplx* wd = w1d + ((size_t)N + (size_t)d * DEEP_BLK_W) * DEEP_BLK_W;
+        #pragma unroll
+        for(int r = 0; r < DEEP_BLK_R; r++) wreg[d][r] = ldg(&wd[(ib * DEEP_BLK_R + r) * DEEP_BLK_W + j]);
+        bias[d] = (j < ly.size) ? ldg(&ly.bias[j]) : cplx(0.0, 0.0);
+    }
+    const unsigned S_last = psi.L[1 + NDEEP].size;
+    if(j < S_last) fw = ldg(&psi.final_w[j]);
+    const cplx* __restrict__ w1 = w1d + j;
+
+    // deep layers + final sum for the first-layer angle `ang` of this thread's unit; log psi of this group's configuration
+    auto forward = [&](cplx ang) -> cplx {
+        actv[c][j] = (j < S1) ? act_lc(ang, 0u) : cplx(0.0, 0.0);
+        __syncthreads();
+        cplx y(0.0, 0.0);
+        #pragma unroll
+        for(int d = 0; d < NDEEP; d++) {
+            cplx p[DEEP_BLK_NC];
+            #pragma unroll
+            for(int cc = 0; cc < DEEP_BLK_NC; cc++) p[cc] = cplx(0.0, 0.0);
+            #pragma unroll
+            for(int r = 0; r < DEEP_BLK_R; r++) {
+                #pragma unroll
+                for(int cc = 0; cc < DEEP_BLK_NC; cc++) cfma(p[cc], wreg[d][r], actv[cc][ib * DEEP_BLK_R + r]);
+            }
+            #pragma unroll
+            for(int cc = 0; cc < DEEP_BLK_NC; cc++) part[cc][ib][j] = p[cc];
+            __syncthreads();
+            const cplx s = ((part[c][0][j] + part[c][1][j]) + (part[c][2][j] + part[c][3][j])) + bias[d];
+            y = (j < psi.L[2 + d].size) ? act_lc(s, (unsigned)d + 1u) : cplx(0.0, 0.0);
+            if(d + 1 < NDEEP) { actv[c][j] = y; __syncthreads(); }
+        }
+        const cplx v = warp_sum(y * fw);
+        if(lane == 0) fin[c][(tid >> 5) & 1u] = v;
+        __syncthreads();
+        return psi.lp + (fin[c][0] + fin[c][1]);
+    };
+
+    for(size_t s = blockIdx.x; s < ns; s += gridDim.x) {
+        uint64_t conf[MAXW];
+        conf_load(conf, confs + s * psi.words, psi.words);
+        cplx ang0(0.0, 0.0);
+        if(j < S1) {
+            const DeepLayerDev& l1 = psi.L[1];
+            for(unsigned i = 0; i < l1.conn; i++) ang0 += conf_spin(conf, l1.lhs_c[i * S1 + j]) * ldg(&l1.lhs_w[i * S1 + j]);
+            ang0 += ldg(&l1.bias[j]);
+        }
+        // diagonal strings over the block; active flip groups compacted by warp 0
+        cplx E(0.0, 0.0);
+        for(unsigned n = tid; n < op.num_diag; n += DEEP_BLK_T) E += string_sign_reg(op, n, conf) * op.coef[n];
+        if(warp == 0) {
+            unsigned count = 0;
+            for(unsigned g0 = 0; g0 < G; g0 += 32u) {
+                const unsigned g = g0 + lane;
+                cplx C(0.0, 0.0);
+                if(g < G) C = strings_coefficient_reg(op, op.group_begin[g], op.group_begin[g + 1u], conf);
+                const bool active = (C.re != 0.0 || C.im != 0.0);
+                const unsigned ballot = __ballot_sync(FULL, active);
+                if(active) { const unsigned pos = count + __popc(ballot & ((1u << lane) - 1u)); list_C[pos] = C; list_g[pos] = g; }
+                count += __popc(ballot);
+            }
+            if(lane == 0) count_sh = count;
+        }
+        const cplx lp = forward(ang0);                       // its barriers also publish the lists and count_sh
+        const unsigned count = count_sh;
+        for(unsigned idx0 = 0; idx0 < count; idx0 += DEEP_BLK_NC) {
+            const unsigned idx = idx0 + c;
+            const bool valid = idx < count;
+            cplx ang = ang0;
+            if(valid) {
+                const unsigned g = list_g[idx];
+                for(unsigned w = 0; w < op.words; w++) {
+                    uint64_t m = op.flip[g * op.words + w];
+                    while(m) {
+                        const unsigned p = w * 64u + (unsigned)__ffsll((long long)m) - 1u;
+                        const double delta = -2.0 * conf_spin(conf, p);
+                        const cplx wv = ldg(&w1[(size_t)p * DEEP_BLK_W]);
+                        ang.re = fma(delta, wv.re, ang.re); ang.im = fma(delta, wv.im, ang.im);
+                        m &= m - 1ull;
+                    }
+                }
+            }
+            const cplx lp2 = forward(ang);
+            if(valid && j == 0u) E += list_C[idx] * cexp(lp2 - lp);
+        }
+        // block sum of E
+        E = warp_sum(E);
+        if(lane == 0) esum[warp] = E;
+        __syncthreads();
+        if(tid == 0) {
+            cplx t(0.0, 0.0);
+            #pragma unroll
+            for(int q = 0; q < DEEP_BLK_T / 32; q++) t += esum[q];
+            eloc_out[s] = t;
+        }
+        __syncthreads();                                     // lists / esum are reused by the next sample
+    }
+}
+
 #endif // __CUDACC__
 
 } // namespace angpu

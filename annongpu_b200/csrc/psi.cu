@@ -375,7 +375,17 @@ void PsiDeep::set_params(const cplx* in) {
     upload();
 }
 void PsiDeep::log_psi(SampleSet& S, bool es_weights) { generic_log_psi(dev(), S, es_weights); }
-void PsiDeep::eloc(const Operator& op, SampleSet& S) { require_operator_fits(op, N, words); generic_eloc(dev(), op, S); }
+void PsiDeep::eloc(const Operator& op, SampleSet& S) {
+    require_operator_fits(op, N, words);
+    if(S.ns == 0) return;
+    const char* env_s = getenv("ANGPU_DEEP_ELOC");              // "generic" forces the warp-per-sample kernel
+    const size_t dyn = (size_t)op.dev.num_groups * (sizeof(cplx) + sizeof(unsigned)) + 16;
+    if(!block_sampler_ok || (env_s && std::string(env_s) == "generic") || op.dev.num_groups == 0 || dyn > 64 * 1024) { generic_eloc(dev(), op, S); return; }
+    const unsigned grid = (unsigned)std::min<size_t>(S.ns, (size_t)ctx().num_sms * 8);
+    if(num_layers == 3u) { set_smem(k_eloc_deep_block<1>, dyn); k_eloc_deep_block<1><<<grid, DEEP_BLK_T, dyn, stream()>>>(dev(), d_w1dense.p, op.dev, S.conf.p, S.ns, S.eloc.p); }
+    else                 { set_smem(k_eloc_deep_block<2>, dyn); k_eloc_deep_block<2><<<grid, DEEP_BLK_T, dyn, stream()>>>(dev(), d_w1dense.p, op.dev, S.conf.p, S.ns, S.eloc.p); }
+    ANGPU_CHECK_LAUNCH(); count_launch();
+}
 void PsiDeep::ok_rows(SampleSet& S, size_t s0, size_t cnt, cplx* out) { generic_ok(dev(), S, s0, cnt, out); }
 void PsiDeep::mc_sample(const McParams& mc, SampleSet& S, unsigned long long* a) {
     const char* env_s = getenv("ANGPU_DEEP_SAMPLER");          // "generic" forces the warp-per-chain kernel (tests, A/B timing)

@@ -550,3 +550,25 @@ def test_cnn_cone_local_energy_bit_identical_to_full_forward(gpu, name):
     for a, b in zip(out["cone"], out["generic"]):
         assert rel_err(a, b) <= 1e-13
     assert np.array_equal(out["cone"][0], out["cone"][2])
+
+
+@pytest.mark.parametrize("name", ["deep2", "deep3", "C4"])
+def test_deep_block_local_energy_matches_generic(gpu, name):
+    """PsiDeep E_loc with register-resident deep layers (block per sample, 4 flip groups per round) against the generic
+    warp-per-sample kernel."""
+    import os
+    if name == "C4":
+        spec, H = F.config_C4()
+        N = 64
+    else:
+        spec, H, N = zoo()[name]
+    psi, op = make_psi(gpu, spec), make_op(gpu, H)
+    confs = _sample_confs(np.random.default_rng(9), N, 37)
+    out = {}
+    try:
+        for mode in ("block", "generic"):
+            os.environ["ANGPU_DEEP_ELOC"] = mode
+            out[mode] = gpu.local_energies(psi, op, confs)[1]
+    finally:
+        os.environ["ANGPU_DEEP_ELOC"] = "block"
+    assert rel_err(out["block"], out["generic"]) <= 1e-11
