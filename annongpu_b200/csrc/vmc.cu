@@ -733,9 +733,9 @@ __global__ void __launch_bounds__(VB_T) k_cg_p_mb(cplx* __restrict__ p, const cp
 }
 // S.v epilogue fused with the CG scalar work: Ap = sum of the column-reduction chunks - conj(Obar) (Obar . p) + shift p,
 // part_pAp[b] = partial sums of conj(p) . Ap; rolls (r.z, |r|^2) of the previous iteration into scal[0]
-__global__ void __launch_bounds__(VB_T) k_sv_finish_cg(const cplx* __restrict__ part, unsigned chunks, const cplx* __restrict__ Obar,
+__global__ void __launch_bounds__(VB_T) k_sv_finish_cg(const cplx* part, unsigned chunks, const cplx* __restrict__ Obar,
         const cplx* __restrict__ part_dot, const cplx* __restrict__ v, const double* __restrict__ diag, double shift_abs, double shift_rel,
-        size_t P, cplx* __restrict__ out, cplx* __restrict__ part_pAp, cplx* scal_roll) {
+        size_t P, cplx* out, cplx* __restrict__ part_pAp, cplx* scal_roll) {      // part may alias out (chunks == 1)
     if(scal_roll && blockIdx.x == 0 && threadIdx.x == 0) scal_roll[0] = scal_roll[2];
     const cplx d = sum_partials_block(part_dot);
     double acc[2] = {0, 0}, red[2];
@@ -1260,10 +1260,10 @@ int TDVP::solve_cg(double tol, unsigned max_iter, double shift_abs, double shift
     cplx* part_pAp = vb_part.p; cplx* part_rr = vb_part.p + VB_BLOCKS; cplx* part_dot = vb_part.p + 2 * VB_BLOCKS;
     k_cg_init<<<1, RED_T, 0, stream()>>>(p, r, minv, n, scal + 0, Ok_dev(), part_dot);
     ANGPU_CHECK_LAUNCH(); count_launch(2);
-    // single process, sample-based products: the S.v epilogue, p.Ap, |r|^2 and Obar.p ride in three fused vector kernels
-    // (5 launches per iteration); otherwise (all-reduce between the halves of S.v, or products on the dense S) the
-    // generic matvec + separate dot product is used
-    const bool fused = !has_allreduce() && !use_S && S.ns > 0;
+    // sample-based products: the S.v epilogue, p.Ap, |r|^2 and Obar.p ride in three fused vector kernels (5 launches per
+    // iteration; with several ranks the per-rank column sums are all-reduced before the epilogue); products on the dense S
+    // use the generic matvec + a separate dot product
+    const bool fused = !use_S && (S.ns > 0 || has_allreduce());
     // convergence is decided on values summed over ranks, so that every rank takes the same decision
     auto read_rs = [&](int slot) -> double {      // |r|^2 = the imaginary slot of the (r.z, |r|^2) pair
         double* chk = d_scal.p + 12;
@@ -1283,7 +1283,13 @@ int TDVP::solve_cg(double tol, unsigned max_iter, double shift_abs, double shift
         for(it = 1; it <= max_iter; it++) {
             if(fused) {
                 rowdot(p);
-                const ColPartials cp = col_reduce_partials(*this, row_a.p, false);
+                ColPartials cp = col_reduce_partials(*this, row_a.p, false);
+                if(has_allreduce()) {
+                    k_sum_chunks<<<grid_for(P), 256, 0, stream()>>>(cp.x, cp.chunks, P, Ap);
+                    ANGPU_CHECK_LAUNCH(); count_launch();
+                    allreduce_sum(reinterpret_cast<double*>(Ap), 2 * n);
+                    cp.x = Ap; cp.chunks = 1u;
+                }
                 k_sv_finish_cg<<<VB_BLOCKS, VB_T, 0, stream()>>>(cp.x, cp.chunks, Ok_dev(), part_dot, p, dg.p, shift_abs, shift_rel, n, Ap,
                                                                   part_pAp, it > 1 ? scal : nullptr);
                 k_cg_xr_mb<<<VB_BLOCKS, VB_T, 0, stream()>>>(x, r, p, Ap, scal, part_pAp, part_rr, minv, n);
