@@ -81,6 +81,13 @@ _SIGNATURES = {
     "angpu_tdvp_destroy": [vp],
     "angpu_tdvp_eval": [vp, vp, vp, vp],
     "angpu_tdvp_eval_F": [vp, vp, vp, vp],
+    "angpu_kl_create": [u32, vp],
+    "angpu_kl_destroy": [vp],
+    "angpu_kl_set_log_psi_scale": [vp, dbl],
+    "angpu_kl_get_state": [vp, vp],
+    "angpu_kl_value": [vp, vp, vp, vp, dbl, vp],
+    "angpu_kl_gradient": [vp, vp, vp, vp, dbl, dbl, vp, vp],
+    "angpu_kl_gradient_with_noise": [vp, vp, vp, vp, dbl, dbl, vp, vp, vp],
     "angpu_hsd_create": [u32, vp],
     "angpu_hsd_destroy": [vp],
     "angpu_hsd_distance": [vp, vp, vp, vp, C.c_int, vp, vp],

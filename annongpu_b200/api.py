@@ -26,7 +26,7 @@ from .factories import PauliSum, masks_to_words, words_for
 __all__ = [
     "PsiRBM", "PsiDeep", "PsiCNN", "PsiClassicalFP_1", "PsiClassicalFP_2", "PsiClassicalANN_1", "PsiClassicalANN_2",
     "PsiFullyPolarized", "Operator", "Spins", "MonteCarloSpins", "ExactSummationSpins", "ExpectationValue", "TDVP",
-    "HilbertSpaceDistance",
+    "HilbertSpaceDistance", "KullbackLeibler",
     "log_psi_s", "psi_O_k", "psi_O_k_vector", "log_psi", "psi_vector", "log_psi_vector", "apply_operator",
     "local_energies", "activation_function", "pauli_apply", "setDevice", "start_profiling", "stop_profiling",
     "synchronize", "launch_count", "set_stream", "measure_fp64_tflops",
@@ -699,6 +699,56 @@ class HilbertSpaceDistance:
         call("angpu_hsd_gradient", self._h, psi._h, psi_prime._h, op._h, int(bool(is_unitary)), spin_ensemble._h, float(nu),
              _p(g), C.byref(d))
         return g, float(d.value)
+
+
+class KullbackLeibler:
+    """KullbackLeibler(num_params, gpu) (pyANNonGPU/main.cpp.template:445-461): ``kl(psi, psi_prime, ensemble, threshold)``,
+    ``kl.gradient(psi, psi_prime, ensemble, nu, threshold) -> (gradient, value)``, ``kl.gradient_with_noise(...) ->
+    (gradient, noise, value)``; properties ``total_weight``, ``mean_deviation``, ``log_psi_scale`` (rw).  Samples are drawn
+    from psi_prime; the mean deviation of one call is subtracted in the next (``last_mean_deviation`` upstream)."""
+
+    def __init__(self, num_params, gpu=True):
+        _require_gpu(gpu)
+        self.num_params = int(num_params)
+        self._h = C.c_void_p()
+        call("angpu_kl_create", self.num_params, C.byref(self._h))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.angpu_kl_destroy(self._h)
+            self._h = None
+
+    def _state(self):
+        out = np.empty(4)
+        call("angpu_kl_get_state", self._h, _p(out))
+        return out
+
+    total_weight = property(lambda self: float(self._state()[0]))
+    mean_deviation = property(lambda self: complex(self._state()[1], self._state()[2]))
+
+    @property
+    def log_psi_scale(self):
+        return float(self._state()[3])
+
+    @log_psi_scale.setter
+    def log_psi_scale(self, value):
+        call("angpu_kl_set_log_psi_scale", self._h, float(value))
+
+    def __call__(self, psi, psi_prime, ensemble, threshold):
+        v = C.c_double()
+        call("angpu_kl_value", self._h, psi._h, psi_prime._h, ensemble._h, float(threshold), C.byref(v))
+        return float(v.value)
+
+    def gradient(self, psi, psi_prime, ensemble, nu, threshold):
+        g, v = np.empty(self.num_params, dtype=np.complex128), C.c_double()
+        call("angpu_kl_gradient", self._h, psi._h, psi_prime._h, ensemble._h, float(nu), float(threshold), _p(g), C.byref(v))
+        return g, float(v.value)
+
+    def gradient_with_noise(self, psi, psi_prime, ensemble, nu, threshold):
+        g, n, v = np.empty(self.num_params, dtype=np.complex128), np.empty(self.num_params), C.c_double()
+        call("angpu_kl_gradient_with_noise", self._h, psi._h, psi_prime._h, ensemble._h, float(nu), float(threshold), _p(g), _p(n),
+             C.byref(v))
+        return g, n, float(v.value)
 
 
 class TDVP:

@@ -14,6 +14,7 @@ struct angpu_ensemble_s { Ensemble e; };
 struct angpu_expval_s   { ExpectationValue ev; std::unique_ptr<TDVP> grad; };
 struct angpu_tdvp_s     { std::unique_ptr<TDVP> t; };
 struct angpu_hsd_s      { std::unique_ptr<HilbertSpaceDistance> h; };
+struct angpu_kl_s       { std::unique_ptr<KullbackLeibler> k; };
 
 static thread_local std::string g_err;
 
@@ -276,6 +277,33 @@ int angpu_hsd_gradient(angpu_hsd_t hsd, angpu_psi_t psi, angpu_psi_t psi_prime, 
                        float nu, double* gradient_out, double* distance_out) {
     API_BEGIN NOTNULL(hsd); NOTNULL(psi); NOTNULL(psi_prime); NOTNULL(op); NOTNULL(ens); NOTNULL(gradient_out); NOTNULL(distance_out);
     *distance_out = hsd->h->gradient(cp(gradient_out), *psi->p, *psi_prime->p, *op->p, is_unitary != 0, ens->e, nu);
+    API_END
+}
+
+// ---- KullbackLeibler
+int angpu_kl_create(unsigned num_params, angpu_kl_t* out) { API_BEGIN NOTNULL(out); *out = new angpu_kl_s{std::unique_ptr<KullbackLeibler>(new KullbackLeibler(num_params))}; API_END }
+int angpu_kl_destroy(angpu_kl_t kl) { API_BEGIN delete kl; API_END }
+int angpu_kl_set_log_psi_scale(angpu_kl_t kl, double scale) { API_BEGIN NOTNULL(kl); kl->k->log_psi_scale = scale; API_END }
+int angpu_kl_get_state(angpu_kl_t kl, double out[4]) {
+    API_BEGIN NOTNULL(kl); NOTNULL(out);
+    out[0] = kl->k->total_weight; out[1] = kl->k->mean_deviation.re; out[2] = kl->k->mean_deviation.im; out[3] = kl->k->log_psi_scale;
+    API_END
+}
+int angpu_kl_value(angpu_kl_t kl, angpu_psi_t psi, angpu_psi_t psi_prime, angpu_ensemble_t ens, double threshold, double* value_out) {
+    API_BEGIN NOTNULL(kl); NOTNULL(psi); NOTNULL(psi_prime); NOTNULL(ens); NOTNULL(value_out);
+    *value_out = kl->k->value(*psi->p, *psi_prime->p, ens->e, threshold);
+    API_END
+}
+int angpu_kl_gradient(angpu_kl_t kl, angpu_psi_t psi, angpu_psi_t psi_prime, angpu_ensemble_t ens, double nu, double threshold,
+                      double* gradient_out, double* value_out) {
+    API_BEGIN NOTNULL(kl); NOTNULL(psi); NOTNULL(psi_prime); NOTNULL(ens); NOTNULL(gradient_out); NOTNULL(value_out);
+    *value_out = kl->k->gradient(cp(gradient_out), *psi->p, *psi_prime->p, ens->e, nu, threshold);
+    API_END
+}
+int angpu_kl_gradient_with_noise(angpu_kl_t kl, angpu_psi_t psi, angpu_psi_t psi_prime, angpu_ensemble_t ens, double nu, double threshold,
+                                 double* gradient_out, double* noise_out, double* value_out) {
+    API_BEGIN NOTNULL(kl); NOTNULL(psi); NOTNULL(psi_prime); NOTNULL(ens); NOTNULL(gradient_out); NOTNULL(noise_out); NOTNULL(value_out);
+    *value_out = kl->k->gradient_with_noise(cp(gradient_out), noise_out, *psi->p, *psi_prime->p, ens->e, nu, threshold);
     API_END
 }
 

@@ -1422,6 +1422,127 @@ double HilbertSpaceDistance::gradient(cplx* result, Psi& psi, Psi& psi_prime, co
     return dist;
 }
 
+// ============================================================================================ KullbackLeibler
+// per sample (KullbackLeibler.cu.template:41-60): weight = w' exp(2 (scale Re log psi - Re log psi')), deviation =
+// log psi' - scale log psi - last_mean_deviation, masked to 0 where |deviation| <= threshold.  The weights are rewritten
+// in place; out6 = {sum weight, Re/Im sum weight (log psi' - scale log psi), Re/Im sum_masked weight dev, sum_masked weight |dev|^2}
+__global__ void __launch_bounds__(RED_T) k_kl_terms(double* __restrict__ w, const cplx* __restrict__ lpp, const cplx* __restrict__ lp, size_t ns,
+        double scale, cplx last_md, double threshold2, cplx* __restrict__ dev_out, double* __restrict__ out6) {
+    double v[6] = {0, 0, 0, 0, 0, 0}, red[6];
+    for(size_t s = threadIdx.x; s < ns; s += RED_T) {
+        const cplx l = scale * lp[s], diff = lpp[s] - l;
+        const double wt = w[s] * exp(2.0 * (l.re - lpp[s].re));
+        w[s] = wt;
+        const cplx d = diff - last_md;
+        const double d2 = abs2(d);
+        const bool keep = d2 > threshold2;
+        dev_out[s] = keep ? d : cplx(0.0, 0.0);
+        v[0] += wt; v[1] += wt * diff.re; v[2] += wt * diff.im;
+        if(keep) { v[3] += wt * d.re; v[4] += wt * d.im; v[5] += wt * d2; }
+    }
+    block_reduce<6>(v, red);
+    if(threadIdx.x == 0) { for(int i = 0; i < 6; i++) out6[i] = red[i]; }
+}
+__global__ void k_kl_factor(const cplx* __restrict__ dev, size_t ns, int which, cplx* __restrict__ out) {     // 0: conj(dev), 1: |dev|^2
+    for(size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < ns; s += (size_t)gridDim.x * blockDim.x)
+        out[s] = which == 0 ? conj(dev[s]) : cplx(abs2(dev[s]), 0.0);
+}
+// column sums with |O_sk|^2 over dense rows: out[0][k] = sum w |O|^2, out[1][k] = sum w |dev|^2 |O|^2, out[2..3][k] = Re/Im sum w dev |O|^2
+__global__ void k_kl_abs2_cols(const cplx* __restrict__ O, const double* __restrict__ w, const cplx* __restrict__ dev, size_t ns, unsigned P,
+                               double* __restrict__ out) {
+    const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+    if(k >= P) return;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    for(size_t s = 0; s < ns; s++) {
+        const double o2 = abs2(O[s * P + k]), wt = w[s];
+        const cplx d = dev[s];
+        a0 += wt * o2; a1 += wt * abs2(d) * o2; a2 += wt * d.re * o2; a3 += wt * d.im * o2;
+    }
+    out[k] = a0; out[(size_t)P + k] = a1; out[2 * (size_t)P + k] = a2; out[3 * (size_t)P + k] = a3;
+}
+
+// mode 0: scalars only; 1: + O_k and dev conj(O_k) sums; 2: + the noise terms (dense rows)
+void KullbackLeibler::averages(Psi& psi, Psi& psi_prime, Ensemble& ens, double threshold, int mode, double h[6]) {
+    ANGPU_REQUIRE(psi.N == psi_prime.N, "KullbackLeibler: psi and psi_prime act on different numbers of sites");
+    ANGPU_REQUIRE(psi_prime.P == P, "KullbackLeibler: num_params differs from psi_prime's");
+    SampleSet& S = rows.S;
+    ens.generate(psi_prime, S);                                   // samples of psi_prime: conf, log psi', w'
+    Sp.resize(S.ns, psi.words);
+    dev.resize(std::max<size_t>(1, S.ns));
+    d_scal.resize(8);
+    if(S.ns) {
+        ANGPU_CUDA(cudaMemcpyAsync(Sp.conf.p, S.conf.p, sizeof(uint64_t) * S.ns * S.words, cudaMemcpyDeviceToDevice, stream()));
+        psi.log_psi(Sp, false);
+    }
+    k_kl_terms<<<1, RED_T, 0, stream()>>>(S.weight.p, S.log_psi.p, Sp.log_psi.p, S.ns, log_psi_scale, last_mean_deviation, threshold * threshold, dev.p, d_scal.p);
+    ANGPU_CHECK_LAUNCH(); count_launch();
+    allreduce_sum(d_scal.p, 6);
+    if(mode >= 1) {
+        g.resize(5 * (size_t)P);                                  // O | dev conj(O) | dev O | |dev|^2 O  (sums over samples)
+        rows.evaluated = true;
+        rows.prepare_rows(psi_prime, mode == 2);
+        col_reduce(rows, dev.p, g.p, g.p + P);                    // mean = sum w O, x = sum w dev conj(O)
+        size_t nsum = 2 * (size_t)P;
+        if(mode == 2) {
+            aux.resize(std::max<size_t>(1, S.ns));
+            k_kl_factor<<<grid_for(S.ns), 256, 0, stream()>>>(dev.p, S.ns, 0, aux.p);
+            col_reduce(rows, aux.p, nullptr, g.p + 2 * P);        // sum w conj(dev) conj(O) = conj(sum w dev O)
+            k_kl_factor<<<grid_for(S.ns), 256, 0, stream()>>>(dev.p, S.ns, 1, aux.p);
+            col_reduce(rows, aux.p, nullptr, g.p + 3 * P);        // sum w |dev|^2 conj(O) = conj(sum w |dev|^2 O)
+            gabs.resize(4 * (size_t)P);
+            k_kl_abs2_cols<<<ceil_div(P, 128), 128, 0, stream()>>>(rows.O.p, S.weight.p, dev.p, S.ns, P, gabs.p);
+            ANGPU_CHECK_LAUNCH(); count_launch(3);
+            allreduce_sum(gabs.p, 4 * (size_t)P);
+            nsum = 4 * (size_t)P;
+        }
+        allreduce_sum(reinterpret_cast<double*>(g.p), 2 * nsum);
+    }
+    d_scal.download(h, 6);
+    total_weight = h[0];
+    mean_deviation = cplx(h[1] / h[0], h[2] / h[0]);              // update_last_mean_deviation (:178-184)
+    last_mean_deviation = mean_deviation;
+}
+static double kl_value(const double h[6]) {
+    const double d_re = h[3] / h[0], d_im = h[4] / h[0], d2 = h[5] / h[0];
+    return std::sqrt(std::max(1e-8, d2 - (d_re * d_re + d_im * d_im)));
+}
+double KullbackLeibler::value(Psi& psi, Psi& psi_prime, Ensemble& ens, double threshold) {
+    double h[6]; averages(psi, psi_prime, ens, threshold, 0, h);
+    return kl_value(h);
+}
+double KullbackLeibler::gradient(cplx* result, Psi& psi, Psi& psi_prime, Ensemble& ens, double nu, double threshold) {
+    double h[6]; averages(psi, psi_prime, ens, threshold, 1, h);
+    const double v = kl_value(h), f = std::pow(v, nu), tw = h[0];
+    const cplx d(h[3] / tw, h[4] / tw);
+    std::vector<cplx> gh(2 * (size_t)P); g.download(gh.data(), gh.size());
+    for(unsigned k = 0; k < P; k++) {                              // :232-236
+        const cplx O = (1.0 / tw) * gh[k], dOc = (1.0 / tw) * gh[P + k];
+        const cplx r = dOc - d * conj(O);
+        result[k] = cplx(r.re / f, r.im / f);
+    }
+    return v;
+}
+double KullbackLeibler::gradient_with_noise(cplx* result, double* noise, Psi& psi, Psi& psi_prime, Ensemble& ens, double nu, double threshold) {
+    double h[6]; averages(psi, psi_prime, ens, threshold, 2, h);
+    const double v = kl_value(h), f = std::pow(v, nu), tw = h[0], d2 = h[5] / tw;
+    const cplx d(h[3] / tw, h[4] / tw);
+    std::vector<cplx> gh(4 * (size_t)P); g.download(gh.data(), gh.size());
+    std::vector<double> ga(4 * (size_t)P); gabs.download(ga.data(), ga.size());
+    const double steps = (double)ens.num_steps();
+    for(unsigned k = 0; k < P; k++) {                              // :286-312
+        const cplx O = (1.0 / tw) * gh[k], dOc = (1.0 / tw) * gh[P + k];
+        const cplx dO = conj((1.0 / tw) * gh[2 * (size_t)P + k]), d2O = conj((1.0 / tw) * gh[3 * (size_t)P + k]);
+        const double O2 = ga[k] / tw, d2O2 = ga[(size_t)P + k] / tw;
+        const cplx dO2(ga[2 * (size_t)P + k] / tw, ga[3 * (size_t)P + k] / tw);
+        const cplx r = dOc - d * conj(O);
+        result[k] = cplx(r.re / f, r.im / f);
+        const cplx mix = dO * conj(d) * conj(O) + 2.0 * (conj(dOc) * d * conj(O)) - d2O * conj(O) - dO2 * conj(d);
+        const double var = d2O2 - abs2(dOc) + 2.0 * mix.re + d2 * abs2(O) + abs2(d) * O2 - 4.0 * abs2(d) * abs2(O);
+        noise[k] = std::sqrt(var / steps) / f;
+    }
+    return v;
+}
+
 // ============================================================================================ FP64 peak probe
 // Dependent-free DFMA streams: 8 independent accumulators per thread, 64k FMAs each. Used by bench.py as the measured
 // denominator for the FP64-pipe-bound kernels (MEASURED_PEAKS.json has no fp64 figure).

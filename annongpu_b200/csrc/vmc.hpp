@@ -134,6 +134,25 @@ private:
     void averages(Psi& psi, Psi& psi_prime, const Operator& op, bool is_unitary, Ensemble& ens, bool want_gradient, double h[5]);
 };
 
+// KullbackLeibler (include/network_functions/KullbackLeibler.hpp:52-124, source/network_functions/KullbackLeibler.cu.template):
+// deviation statistics of log psi' - scale * log psi on samples of psi', and their gradient with respect to psi'.
+struct KullbackLeibler {
+    unsigned P;                                  // parameters of psi_prime
+    double log_psi_scale = 1.0;
+    cplx   last_mean_deviation{0.0, 0.0}, mean_deviation{0.0, 0.0};
+    double total_weight = 0.0;
+    TDVP rows;                                   // rows.S = samples of psi_prime with the reweighted weights
+    SampleSet Sp;                                // log psi at the same configurations
+    DevBuf<cplx> dev, aux, g;                    // per-sample masked deviation; scratch factor; [k][P] column sums
+    DevBuf<double> d_scal, gabs;
+    explicit KullbackLeibler(unsigned P_) : P(P_), rows(P_) {}
+    double value(Psi& psi, Psi& psi_prime, Ensemble& ens, double threshold);
+    double gradient(cplx* result_host, Psi& psi, Psi& psi_prime, Ensemble& ens, double nu, double threshold);
+    double gradient_with_noise(cplx* result_host, double* noise_host, Psi& psi, Psi& psi_prime, Ensemble& ens, double nu, double threshold);
+private:
+    void averages(Psi& psi, Psi& psi_prime, Ensemble& ens, double threshold, int mode, double h[6]);
+};
+
 // free functions (source/network_functions/{PsiVector,PsiNorm,PsiOkVector,ApplyOperator}.cu.template)
 cplx   log_psi_s(Psi& psi, const uint64_t* conf);
 void   psi_O_k(Psi& psi, const uint64_t* conf, cplx* out_host);

@@ -34,6 +34,7 @@ typedef struct angpu_ensemble_s* angpu_ensemble_t;   /* MonteCarloSpins | ExactS
 typedef struct angpu_expval_s*   angpu_expval_t;     /* ExpectationValue */
 typedef struct angpu_tdvp_s*     angpu_tdvp_t;       /* TDVP */
 typedef struct angpu_hsd_s*      angpu_hsd_t;        /* HilbertSpaceDistance */
+typedef struct angpu_kl_s*       angpu_kl_t;         /* KullbackLeibler */
 
 enum { ANGPU_PSI_RBM = 0, ANGPU_PSI_DEEP = 1, ANGPU_PSI_CNN = 2, ANGPU_PSI_CLASSICAL = 3 };
 
@@ -200,6 +201,23 @@ int angpu_hsd_distance(angpu_hsd_t hsd, angpu_psi_t psi, angpu_psi_t psi_prime, 
                        angpu_ensemble_t ens, double* distance_out);
 int angpu_hsd_gradient(angpu_hsd_t hsd, angpu_psi_t psi, angpu_psi_t psi_prime, angpu_operator_t op, int is_unitary,
                        angpu_ensemble_t ens, float nu, double* gradient_out, double* distance_out);
+
+/* ---- KullbackLeibler(num_params, gpu)  (include/network_functions/KullbackLeibler.hpp:52-124,
+ * source/network_functions/KullbackLeibler.cu.template:16-321; pyANNonGPU/main.cpp.template:445-461).
+ * Samples s ~ |psi'|^2 (psi_prime); weight_s = w'_s |psi(s)^scale / psi'(s)|^2; deviation_s = log psi'(s) - scale log psi(s)
+ * - last_mean_deviation (the weighted mean of the previous call, kept in the object); samples with |deviation| <= threshold
+ * are left out of the deviation sums.  value = sqrt(max(1e-8, <|dev|^2> - |<dev>|^2)); gradient_k = (<dev conj(O'_k)> -
+ * <dev> conj(<O'_k>)) / value^nu with respect to psi_prime's parameters; noise_k = its sampling error estimate
+ * (dense rows of psi_prime).  The reference binds psi = PsiClassical*, psi_prime = PsiDeep | PsiCNN; any pair works here. */
+int angpu_kl_create(unsigned num_params, angpu_kl_t* out);
+int angpu_kl_destroy(angpu_kl_t kl);
+int angpu_kl_set_log_psi_scale(angpu_kl_t kl, double scale);
+int angpu_kl_get_state(angpu_kl_t kl, double out[4]);        /* total_weight, Re/Im mean_deviation, log_psi_scale */
+int angpu_kl_value(angpu_kl_t kl, angpu_psi_t psi, angpu_psi_t psi_prime, angpu_ensemble_t ens, double threshold, double* value_out);
+int angpu_kl_gradient(angpu_kl_t kl, angpu_psi_t psi, angpu_psi_t psi_prime, angpu_ensemble_t ens, double nu, double threshold,
+                      double* gradient_out, double* value_out);
+int angpu_kl_gradient_with_noise(angpu_kl_t kl, angpu_psi_t psi, angpu_psi_t psi_prime, angpu_ensemble_t ens, double nu,
+                                 double threshold, double* gradient_out, double* noise_out, double* value_out);
 
 #ifdef __cplusplus
 }

@@ -448,6 +448,53 @@ def hilbert_space_distance_gradient(psi, psi_prime, op, is_unitary, ens, nu):
     return -(u_k * v - u * v_k) / (v * v) / prefactor, distance
 
 
+class KullbackLeibler:
+    """Restatement of KullbackLeibler (source/network_functions/KullbackLeibler.cu.template:16-321): samples from psi_prime,
+    weights w' |psi^scale / psi'|^2, deviation = log psi' - scale log psi - last_mean_deviation (the latter carried from
+    the previous call), terms with |deviation| <= threshold dropped from the deviation sums."""
+
+    def __init__(self, num_params):
+        self.num_params, self.log_psi_scale = int(num_params), 1.0
+        self.last_mean_deviation, self.mean_deviation, self.total_weight = 0j, 0j, 0.0
+
+    def _averages(self, psi, psi_prime, ens, threshold, want_O):
+        confs, lpp, wp = _samples_and_weights(psi_prime, ens)
+        lp = eval_samples(psi, None, confs)[0] * self.log_psi_scale
+        w = wp * np.exp(2.0 * (lp.real - lpp.real))
+        tw = np.sum(w)
+        dev = lpp - lp - self.last_mean_deviation
+        dev2 = np.abs(dev) ** 2
+        keep = dev2 > threshold * threshold
+        out = {"tw": tw, "mean_dev": np.sum(w * (lpp - lp)) / tw, "d": np.sum((w * dev)[keep]) / tw, "d2": np.sum((w * dev2)[keep]) / tw}
+        if want_O:
+            O = eval_samples(psi_prime, None, confs, want_O=True)[2]
+            wk, O2 = np.where(keep, w, 0.0), np.abs(O) ** 2
+            out.update(O=(w @ O) / tw, dOc=((wk * dev) @ np.conj(O)) / tw, d2O2=((wk * dev2) @ O2) / tw, dO=((wk * dev) @ O) / tw,
+                       dO2=((wk * dev) @ O2) / tw, d2O=((wk * dev2) @ O) / tw, O2=(w @ O2) / tw)
+        self.total_weight, self.mean_deviation = float(tw), complex(out["mean_dev"])
+        self.last_mean_deviation = self.mean_deviation
+        out["value"] = float(np.sqrt(max(1e-8, out["d2"] - abs(out["d"]) ** 2)))
+        return out
+
+    def __call__(self, psi, psi_prime, ens, threshold):
+        return self._averages(psi, psi_prime, ens, threshold, False)["value"]
+
+    def gradient(self, psi, psi_prime, ens, nu, threshold):
+        a = self._averages(psi, psi_prime, ens, threshold, True)
+        return (a["dOc"] - a["d"] * np.conj(a["O"])) / a["value"] ** nu, a["value"]
+
+    def gradient_with_noise(self, psi, psi_prime, ens, nu, threshold):
+        a = self._averages(psi, psi_prime, ens, threshold, True)
+        f = a["value"] ** nu
+        d, d2, O = a["d"], a["d2"], a["O"]
+        var = (a["d2O2"] - np.abs(a["dOc"]) ** 2 + 2.0 * (a["dO"] * np.conj(d) * np.conj(O) + 2.0 * np.conj(a["dOc"]) * d * np.conj(O)
+                                                              - a["d2O"] * np.conj(O) - a["dO2"] * np.conj(d)).real
+               + d2 * np.abs(O) ** 2 + abs(d) ** 2 * a["O2"] - 4.0 * abs(d) ** 2 * np.abs(O) ** 2)
+        with np.errstate(invalid="ignore"):
+            noise = np.sqrt(var / ens.num_steps) / f
+        return (a["dOc"] - d * np.conj(O)) / f, noise, a["value"]
+
+
 class TDVP:
     def __init__(self, num_params):
         self.P = int(num_params)

@@ -83,6 +83,8 @@ def lib():
         L.ref_tdvp_eval_with_psi_ref.restype = dbl
         L.ref_hilbert_space_distance.argtypes = [i32, vp, vp, vp, i32, i32, vp, vp, C.c_float]
         L.ref_hilbert_space_distance.restype = dbl
+        L.ref_kullback_leibler.argtypes = [i32, vp, i32, vp, i32, vp, i32, dbl, dbl, dbl, dbl, dbl, vp, vp, vp]
+        L.ref_kullback_leibler.restype = dbl
         L.ref_set_gpu.argtypes = [i32]
         L.ref_device_synchronize.restype = i32
         _lib = L
@@ -358,6 +360,36 @@ def hilbert_space_distance_gradient(psi, psi_prime, op, is_unitary, ens, nu):
     g = _cout(psi_prime.num_params)
     d = lib().ref_hilbert_space_distance(psi.kind, psi.h, psi_prime.h, op.h, int(bool(is_unitary)), ens.kind, ens.h, _p(g), float(nu))
     return g, float(d)
+
+
+class KullbackLeibler:
+    """KullbackLeibler(num_params, gpu) (pyANNonGPU/main.cpp.template:445-461): psi a PsiClassical kind, psi_prime a PsiDeep
+    or PsiCNN; samples are drawn from psi_prime.  last_mean_deviation is carried from call to call like upstream."""
+
+    def __init__(self, num_params):
+        self.num_params, self.log_psi_scale = int(num_params), 1.0
+        self.last_mean_deviation, self.mean_deviation, self.total_weight = 0j, 0j, 0.0
+
+    def _run(self, mode, psi, psi_prime, ens, nu, threshold):
+        assert psi_prime.kind in (DEEP, CNN) and psi.kind in (CLFP1, CLFP2, CLANN1, CLANN2)
+        g, noise, extra = _cout(self.num_params), np.zeros(self.num_params), np.zeros(3)
+        v = lib().ref_kullback_leibler(psi.kind, psi.h, psi_prime.kind, psi_prime.h, ens.kind, ens.h, mode, float(nu), float(threshold),
+                                       float(self.log_psi_scale), self.last_mean_deviation.real, self.last_mean_deviation.imag,
+                                       _p(g), _p(noise), _p(extra))
+        self.total_weight, self.mean_deviation = float(extra[0]), complex(extra[1], extra[2])
+        self.last_mean_deviation = self.mean_deviation
+        return float(v), g, noise
+
+    def __call__(self, psi, psi_prime, ens, threshold):
+        return self._run(0, psi, psi_prime, ens, 0.0, threshold)[0]
+
+    def gradient(self, psi, psi_prime, ens, nu, threshold):
+        v, g, _ = self._run(1, psi, psi_prime, ens, nu, threshold)
+        return g, v
+
+    def gradient_with_noise(self, psi, psi_prime, ens, nu, threshold):
+        v, g, noise = self._run(2, psi, psi_prime, ens, nu, threshold)
+        return g, noise, v
 
 
 class TDVP:

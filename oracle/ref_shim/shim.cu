@@ -29,6 +29,7 @@
 #include "network_functions/PsiOkVector.hpp"
 #include "network_functions/ApplyOperator.hpp"
 #include "network_functions/HilbertSpaceDistance.hpp"
+#include "network_functions/KullbackLeibler.hpp"
 #include "quantum_states.hpp"
 #include "quantum_state/psi_functions.hpp"
 #include "ensembles.hpp"
@@ -354,6 +355,39 @@ double ref_hilbert_space_distance(int kind, void* h, void* h_prime, void* op, in
     if(kind == DEEP) run(*static_cast<PsiDeep*>(h), *static_cast<PsiDeep*>(h_prime));
     else if(kind == CNN) run(*static_cast<PsiCNN*>(h), *static_cast<PsiCNN*>(h_prime));
     return d;
+}
+
+// ---------------------------------------------------------------- KullbackLeibler
+// (include/network_functions/KullbackLeibler.hpp:52-124; psi: a PsiClassical kind, psi_prime: PsiDeep or PsiCNN.)
+// mode 0: value, 1: gradient, 2: gradient_with_noise.  last_md: last_mean_deviation carried in from a previous call.
+// extra_out = {total_weight, Re mean_deviation, Im mean_deviation} after the call.  Returns the value.
+double ref_kullback_leibler(int kind, void* h, int pkind, void* hp, int ek, void* e, int mode, double nu, double threshold,
+                            double log_psi_scale, double last_md_re, double last_md_im,
+                            double* grad_out, double* noise_out, double* extra_out) {
+    double v = 0.0;
+    auto run = [&](auto& psi, auto& psi_prime) {
+        KullbackLeibler kl(psi_prime.num_params, g_gpu);
+        kl.log_psi_scale = log_psi_scale;
+        kl.last_mean_deviation.front() = complex_t(last_md_re, last_md_im);
+        kl.last_mean_deviation.update_device();
+        with_ens(ek, e, [&](auto& ens) {
+            if(mode == 0) v = kl.value(psi, psi_prime, ens, threshold);
+            else if(mode == 1) v = kl.gradient(reinterpret_cast<std::complex<double>*>(grad_out), psi, psi_prime, ens, nu, threshold);
+            else {
+                auto r = kl.gradient_with_noise(psi, psi_prime, ens, nu, threshold);
+                copy_out(grad_out, std::get<0>(r));
+                std::memcpy(noise_out, std::get<1>(r).host_data(), sizeof(double) * psi_prime.num_params);
+                v = std::get<2>(r);
+            }
+        });
+        extra_out[0] = kl.total_weight.front();
+        store(extra_out + 1, kl.mean_deviation.front());
+    };
+    with_classical(kind, h, [&](auto& psi) {
+        if(pkind == DEEP) run(psi, *static_cast<PsiDeep*>(hp));
+        else if(pkind == CNN) run(psi, *static_cast<PsiCNN*>(hp));
+    });
+    return v;
 }
 
 // ---------------------------------------------------------------- TDVP

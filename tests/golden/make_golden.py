@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
-from helpers import classical_zoo, hsd_cases, make_classical, make_op, make_psi, zoo   # noqa: E402
+from helpers import classical_zoo, hsd_cases, kl_cases, kl_sequence, make_classical, make_op, make_psi, zoo   # noqa: E402
 from oracle import ref_oracle as R                                           # noqa: E402
 
 PROBES = [0x2A5, 0x13, 0x3FF, 0x0]
@@ -71,6 +71,10 @@ def main():
         out[f"hsd/{name}/distance"] = R.hilbert_space_distance(psi, psi_prime, op, is_unitary, es)
         g, d = R.hilbert_space_distance_gradient(psi, psi_prime, op, is_unitary, es, 1.0)
         out[f"hsd/{name}/gradient"], out[f"hsd/{name}/distance_g"] = g, d
+    # KullbackLeibler (psi: PsiClassical kinds, psi_prime: PsiDeep | PsiCNN): three consecutive calls, helpers.kl_sequence()
+    for name in kl_cases():
+        for k, v in kl_sequence(R, name, R.ExactSummation).items():
+            out[f"kl/{name}/{k}"] = v
     # primitives: Pauli action (bit-exact) and activation polynomials
     rng = np.random.default_rng(7)
     a, b, c = (rng.integers(0, 1 << 63, size=64, dtype=np.uint64) for _ in range(3))

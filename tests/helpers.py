@@ -108,6 +108,30 @@ def hsd_cases():
     }
 
 
+def kl_cases():
+    """name -> (classical zoo entry name, spec of psi_prime) for KullbackLeibler (psi: PsiClassical, psi_prime: Deep | CNN)."""
+    deep_p = F.deep_spec(6, 6, [12, 6], [6, 12], noise=5e-2, a=0.05, final_weights=2, seed=33)
+    cnn_p = F.cnn_spec([1, 2, 3], [(2, [1, 2, 2]), (2, [1, 2, 2])], noise=2e-1, final_factor=2, seed=34)
+    return {"clfp1_deep": ("clfp1", deep_p), "clfp2_cnn": ("clfp2", cnn_p), "clann1_cnn": ("clann1", cnn_p), "clann2_deep": ("clann2", deep_p)}
+
+
+def kl_sequence(mod, name, ensemble_cls):
+    """Three consecutive calls on one KullbackLeibler object (the mean deviation is carried from call to call):
+    value(threshold 0), gradient(nu 0.5, threshold 1e-3), gradient_with_noise(nu 1, threshold 0)."""
+    cname, pspec = kl_cases()[name]
+    N, order, Hl, pr, ref_spec, lp, H = classical_zoo()[cname]
+    psi, psi_prime = make_classical(mod, N, order, Hl, pr, ref_spec, lp), make_psi(mod, pspec)
+    if hasattr(psi_prime, "init_gradient"):
+        psi_prime.init_gradient(1 << N)
+    es = ensemble_cls(N)
+    kl = mod.KullbackLeibler(psi_prime.num_params) if mod.__name__.endswith("oracle") else mod.KullbackLeibler(psi_prime.num_params, True)
+    kl.log_psi_scale = 0.9
+    v1 = kl(psi, psi_prime, es, 0.0)
+    g, v2 = kl.gradient(psi, psi_prime, es, 0.5, 1e-3)
+    gn, noise, v3 = kl.gradient_with_noise(psi, psi_prime, es, 1.0, 0.0)
+    return dict(v1=v1, v2=v2, v3=v3, g=g, gn=gn, noise=noise, total_weight=kl.total_weight, mean_deviation=kl.mean_deviation)
+
+
 class GpuAdapter:
     """Presents annongpu_b200 with the oracle modules' function names, so one checker serves both."""
     __name__ = "annongpu_b200"
@@ -116,7 +140,7 @@ class GpuAdapter:
         self.A = A
         self.ev = A.ExpectationValue(True)
         for k in ("PsiRBM", "PsiDeep", "PsiCNN", "PsiClassicalFP_1", "PsiClassicalFP_2", "PsiClassicalANN_1", "PsiClassicalANN_2",
-                  "PsiFullyPolarized", "Operator", "log_psi", "psi_vector", "apply_operator"):
+                  "PsiFullyPolarized", "Operator", "log_psi", "psi_vector", "apply_operator", "KullbackLeibler"):
             setattr(self, k, getattr(A, k))
 
     def ExactSummation(self, N):

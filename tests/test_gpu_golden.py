@@ -2,8 +2,9 @@
 import numpy as np
 import pytest
 
-from helpers import GpuAdapter, classical_zoo, hsd_cases, make_classical, make_psi, zoo
-from test_oracle_pinned import GOLDEN, check_against_golden, check_hsd_against_golden, check_wref_against_golden
+from helpers import GpuAdapter, classical_zoo, hsd_cases, kl_cases, make_classical, make_psi, zoo
+from test_oracle_pinned import (GOLDEN, check_against_golden, check_hsd_against_golden, check_kl_against_golden,
+                                check_wref_against_golden)
 
 pytestmark = pytest.mark.gpu
 
@@ -28,6 +29,12 @@ def test_gpu_matches_reference_golden_classical(gpu, name):
 def test_gpu_hilbert_space_distance_matches_reference_golden(gpu, name):
     ad = GpuAdapter(gpu)
     check_hsd_against_golden(ad, name, ad.ExactSummation)
+
+
+@pytest.mark.parametrize("name", sorted(kl_cases()))
+def test_gpu_kullback_leibler_matches_reference_golden(gpu, name):
+    ad = GpuAdapter(gpu)
+    check_kl_against_golden(ad, name, ad.ExactSummation)
 
 
 def test_gpu_primitives_match_golden(gpu):

@@ -572,3 +572,27 @@ def test_deep_block_local_energy_matches_generic(gpu, name):
     finally:
         os.environ["ANGPU_DEEP_ELOC"] = "block"
     assert rel_err(out["block"], out["generic"]) <= 1e-11
+
+
+# ------------------------------------------------------------------------------------------------ SURVEY 8f rank 3 (KullbackLeibler)
+
+def test_kullback_leibler_monte_carlo_and_rbm_prime(gpu, port):
+    """KullbackLeibler on Monte-Carlo samples (identical chains) and with a PsiRBM as psi_prime (factorised rows), which
+    the reference does not instantiate; the state carried between calls (mean deviation) must agree as well."""
+    N, order, Hl, pr, ref_spec, lp, H = classical_zoo()["clfp2"]
+    spec_p = F.rbm_spec(6, 12, noise=5e-2, final_weight=2, seed=51)
+    pg, pp = make_classical(gpu, N, order, Hl, pr, ref_spec, lp), make_classical(port, N, order, Hl, pr, ref_spec, lp)
+    qg, qp = make_psi(gpu, spec_p), make_psi(port, spec_p)
+    kg, kp = gpu.KullbackLeibler(qg.num_params, True), port.KullbackLeibler(qp.num_params)
+    for call in range(2):
+        mg, mp = gpu.MonteCarloSpins(512, 1, 4, 64, True, seed=3 + call), port.MonteCarlo(512, 1, 4, 64, seed=3 + call)
+        g_g, v_g = kg.gradient(pg, qg, mg, 1.0, 0.0)
+        g_p, v_p = kp.gradient(pp, qp, mp, 1.0, 0.0)
+        assert abs(v_g - v_p) <= 1e-9 * max(1.0, v_p) and rel_err(g_g, g_p) <= 1e-8
+        assert abs(kg.mean_deviation - kp.mean_deviation) <= 1e-9 and abs(kg.total_weight - kp.total_weight) <= 1e-9 * kp.total_weight
+    eg, ep = gpu.ExactSummationSpins(N), port.ExactSummation(N)
+    gn_g, n_g, v_g = kg.gradient_with_noise(pg, qg, eg, 0.0, 1e-2)
+    gn_p, n_p, v_p = kp.gradient_with_noise(pp, qp, ep, 0.0, 1e-2)
+    assert abs(v_g - v_p) <= 1e-9 * max(1.0, v_p) and rel_err(gn_g, gn_p) <= 1e-8
+    ok = np.isfinite(n_p)
+    assert np.array_equal(np.isfinite(n_g), ok) and np.allclose(n_g[ok], n_p[ok], rtol=1e-6, atol=1e-12)

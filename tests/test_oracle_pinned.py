@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from annongpu_b200 import factories as F
-from helpers import classical_zoo, hsd_cases, make_classical, make_op, make_psi, rel_err, zoo
+from helpers import classical_zoo, hsd_cases, kl_cases, kl_sequence, make_classical, make_op, make_psi, rel_err, zoo
 
 GOLDEN = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_golden.npz"))
 PROBES = [0x2A5, 0x13, 0x3FF, 0x0]
@@ -78,6 +78,29 @@ def check_hsd_against_golden(mod, name, ensemble_cls):
 @pytest.mark.parametrize("name", sorted(hsd_cases()))
 def test_port_hilbert_space_distance_matches_reference_golden(port, name):
     check_hsd_against_golden(port, name, port.ExactSummation)
+
+
+def check_kl_against_golden(mod, name, ensemble_cls):
+    got = kl_sequence(mod, name, ensemble_cls)
+    g = lambda k: GOLDEN[f"kl/{name}/{k}"]   # noqa: E731
+    for k in ("v1", "v2", "v3"):
+        assert abs(got[k] - g(k)) <= 1e-9 * max(1.0, abs(g(k))), k
+    assert rel_err(got["g"], g("g")) <= 1e-8 and rel_err(got["gn"], g("gn")) <= 1e-8
+    assert abs(got["total_weight"] - g("total_weight")) <= TOL * g("total_weight")
+    assert abs(got["mean_deviation"] - g("mean_deviation")) <= 1e-9 * max(1.0, abs(g("mean_deviation")))
+    if name.endswith("_cnn"):
+        # PsiCNN::foreach_O_k emits a parameter several times (one partial per lattice site, PsiCNN.hpp:185-266);
+        # upstream squares each partial in the noise sums, which is not a function of O_k: the noise is not compared
+        return
+    ref_noise = g("noise")
+    ok = np.isfinite(ref_noise)                       # the upstream variance estimate can be negative (sqrt -> nan)
+    assert np.array_equal(np.isfinite(got["noise"]), ok)
+    assert np.allclose(got["noise"][ok], ref_noise[ok], rtol=1e-6, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", sorted(kl_cases()))
+def test_port_kullback_leibler_matches_reference_golden(port, name):
+    check_kl_against_golden(port, name, port.ExactSummation)
 
 
 def test_port_primitives_match_golden(port):
