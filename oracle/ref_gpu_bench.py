@@ -15,7 +15,7 @@ import subprocess
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))   # repo root (this file lives in oracle/: test infrastructure)
 sys.path.insert(0, ROOT)
 
 

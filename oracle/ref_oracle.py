@@ -93,7 +93,7 @@ def lib():
 
 def set_gpu(on):
     """Objects created afterwards use the reference's own CUDA path (gpu=true).  Timing baseline only
-    (tools/ref_gpu_bench.py); the parity oracle is the default gpu=false host path."""
+    (oracle/ref_gpu_bench.py); the parity oracle is the default gpu=false host path."""
     lib().ref_set_gpu(1 if on else 0)
 
 

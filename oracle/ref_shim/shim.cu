@@ -5,7 +5,7 @@
 // serial host path (gpu=false) is exercised: that path makes no CUDA calls and is the bit-for-bit
 // CPU restatement of the reference's own arithmetic (include/cuda_kernel_defines.h:16-29).
 // ref_set_gpu(1) switches every object created afterwards to the reference's own CUDA path
-// (gpu=true): used ONLY by tools/ref_gpu_bench.py to time the reference's kernels on the same B200
+// (gpu=true): used ONLY by oracle/ref_gpu_bench.py to time the reference's kernels on the same B200
 // as a second baseline.
 //
 // This file contains no reference source: it only *calls* the reference's public C++ API
