@@ -138,7 +138,7 @@ def main():
         ms = timed(lambda: t.eval_F(op, psi, mc), args.steps, warmup=1)
         ph = t.phase_ms
         cg_runs = []
-        for _ in range(3):                       # the per-iteration time of this solve varies run to run (2.9-4.3 ms seen)
+        for _ in range(3):                       # the first solve of a process carries ~150 ms of one-time costs (kernel loading, workspaces)
             x, it, rr = t.solve_cg(tol=1e-6, max_iter=2000, shift_abs=0.0, shift_rel=1e-3)
             cg_runs.append(t.phase_ms["solve"])
         ms_cg = min(cg_runs)
