@@ -44,7 +44,7 @@ def main():
     import annongpu_b200 as A
     from annongpu_b200 import factories as F
     from annongpu_b200 import distributed as D
-    D.init_from_env()
+    rank, world = D.init_from_env()
     fp64_peak = A.measure_fp64_tflops()
     todo = args.configs.split(",")
 
@@ -131,8 +131,10 @@ def main():
     if "C5" in todo:
         spec, H = F.config_C5()
         psi, op = spec.build(True), H.build(True)
-        chains = max(148, int(16384 * args.scale))
+        chains = max(148, int(16384 * args.scale)) * world       # under torchrun: 16384 chains per GPU (8 GPUs = BASELINE config 5)
         mc = A.MonteCarloSpins(chains, 1, 10, chains, True, seed=5)
+        if world > 1:
+            mc.set_shard(rank, world)
         t = A.TDVP(psi.num_params, True)
         t.set_profile(True)
         ms = timed(lambda: t.eval_F(op, psi, mc), args.steps, warmup=1)
@@ -142,7 +144,8 @@ def main():
             x, it, rr = t.solve_cg(tol=1e-6, max_iter=2000, shift_abs=0.0, shift_rel=1e-3)
             cg_runs.append(t.phase_ms["solve"])
         ms_cg = min(cg_runs)
-        print(json.dumps({"config": "C5 (one GPU's shard)", "what": "PsiRBM 200x1600 (P=320000), Heisenberg ring (600 strings), 10+1 sweeps, "
+        if rank == 0:
+          print(json.dumps({"config": "C5 (one GPU's shard)" if world == 1 else f"C5 on {world} GPUs", "n_gpus": world, "what": "PsiRBM 200x1600 (P=320000), Heisenberg ring (600 strings), 10+1 sweeps, "
                           "eval_F + matrix-free CG (tol 1e-6, shift 1e-3 diag)", "chains": chains, "ms_eval_F": ms,
                           "samples_per_s": chains / (ms * 1e-3), "phase_ms": ph, "cg_iterations": it, "cg_rel_residual": rr, "ms_cg": ms_cg,
                           "ms_per_cg_iteration": ms_cg / max(1, it), "ms_cg_runs": cg_runs, "sr_steps_per_s": 1e3 / (ms + ms_cg),
