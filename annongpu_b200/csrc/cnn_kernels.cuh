@@ -86,7 +86,9 @@ __device__ __forceinline__ cplx cnn_log_psi_resident(const CnnDev& psi, const cp
     const cplx* o = act + last.angle_off;
     cplx r(0.0, 0.0);
     for(unsigned idx = lane; idx < last.nch * psi.N; idx += 32u) r += o[idx];
-    return psi.lp + psi.final_factor * warp_sum(r);
+    const cplx total = warp_sum(r);
+    __syncwarp();                       // the callers overwrite the activations next (restore / next proposal)
+    return psi.lp + psi.final_factor * total;
 }
 
 __global__ void __launch_bounds__(128)
