@@ -191,9 +191,10 @@ void PsiRBM::ok_rows(SampleSet& S, size_t s0, size_t cnt, cplx* out) {
 template<int K, int WORDS>
 static void launch_mc_rbm(const RbmDev& d, const cplx* Wp, const McParams& mc, SampleSet& S, unsigned long long* acc_rej_dev) {
     const unsigned wpb = MC_RBM_THREADS / 32, grid = ceil_div(mc.num_chains_local, wpb);
-    // resident blocks per SM requested from ptxas: 8 (<= 128 registers) by default; ANGPU_MC_MINB=10 trades a few spills
-    // for 20 warps per SM (experiment knob, K = 8 with one-word configurations only)
-    static const int minb = [] { const char* e = getenv("ANGPU_MC_MINB"); return e ? atoi(e) : 8; }();
+    // resident blocks per SM requested from ptxas: 8 (<= 128 registers); for K = 8 with one-word configurations (the C2
+    // shape) 10 blocks = 20 warps per SM fit in 96 registers now that the W row is re-read on rejection instead of being
+    // kept live (1.79 -> 1.77 ms per 8192 chains, and 2.77 instead of 3.46 waves).  ANGPU_MC_MINB=8 selects the 8-block build.
+    static const int minb = [] { const char* e = getenv("ANGPU_MC_MINB"); return e ? atoi(e) : 10; }();
     constexpr int DEF = (K <= 8) ? 8 : 1;
     if(K == 8 && WORDS == 1 && minb == 10) {
         if(d.fw.im == 0.0) k_mc_rbm<K, WORDS, true, (K == 8 && WORDS == 1) ? 10 : DEF><<<grid, wpb * 32, 0, stream()>>>(d, Wp, mc, S.conf.p, S.log_psi.p, S.angles.p, acc_rej_dev);

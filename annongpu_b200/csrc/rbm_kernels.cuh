@@ -86,6 +86,16 @@ __device__ __forceinline__ double lc0_re_pq(double x, double y) {
     const double B = fma(p, -12.0 / 45.0, 1.0 / 3.0);
     return fma(q2, B, A * p);
 }
+// acc += Re lc0(x + i y) with the final product and the accumulation folded into two FMAs (one DMUL and one DADD fewer
+// per hidden unit than `acc += lc0_re_pq(x, y)`: 10 instead of 12 FP64 instructions incl. the angle update)
+__device__ __forceinline__ void lc0_re_pq_acc(double x, double y, double& acc) {
+    const double p = fma(x, x, -(y * y)), q = x * y, q2 = q * q;
+    double A = fma(p, 1.0 / 45.0, -1.0 / 12.0);
+    A = fma(A, p, 0.5);
+    const double B = fma(p, -12.0 / 45.0, 1.0 / 3.0);
+    acc = fma(q2, B, acc);
+    acc = fma(A, p, acc);
+}
 __device__ __forceinline__ cplx lc0_pq(double x, double y) {
     const double p = fma(x, x, -(y * y)), q = x * y, q2 = q * q;
     double A = fma(p, 1.0 / 45.0, -1.0 / 12.0);
@@ -157,10 +167,10 @@ k_mc_rbm(const RbmDev psi, const cplx* __restrict__ Wp, const McParams mc, uint6
     }
     auto re_log_psi = [&]() -> double {
         if(FW_REAL) {
-            double p = 0.0;
+            double p0 = 0.0, p1 = 0.0;                       // two accumulation chains
             #pragma unroll
-            for(int k = 0; k < K; k++) p += lc0_re_pq(th[k].re, th[k].im);
-            return fma(psi.fw.re, warp_sum(p), psi.lp.re);
+            for(int k = 0; k < K; k++) { if(k & 1) lc0_re_pq_acc(th[k].re, th[k].im, p1); else lc0_re_pq_acc(th[k].re, th[k].im, p0); }
+            return fma(psi.fw.re, warp_sum(p0 + p1), psi.lp.re);
         } else {
             cplx p(0.0, 0.0);
             #pragma unroll
@@ -199,9 +209,13 @@ k_mc_rbm(const RbmDev psi, const cplx* __restrict__ Wp, const McParams mc, uint6
                 conf_flip_t<WORDS>(conf, site);
                 acc++;
             } else {
-                // undo, as the reference does on rejection (update_input_units(next -> current), MonteCarlo.hpp:173-175)
+                // undo, as the reference does on rejection (update_input_units(next -> current), MonteCarlo.hpp:173-175).
+                // The row is read again (an L1 hit) instead of being kept in 4 K registers across the evaluation above.
                 #pragma unroll
-                for(int k = 0; k < K; k++) { th[k].re = fma(-delta, w[k].re, th[k].re); th[k].im = fma(-delta, w[k].im, th[k].im); }
+                for(int k = 0; k < K; k++) {
+                    const cplx wk = ldg(&row[32u * k]);
+                    th[k].re = fma(-delta, wk.re, th[k].re); th[k].im = fma(-delta, wk.im, th[k].im);
+                }
             }
             if(t0 + b + 1u == next_record) {
                 const size_t idx = (size_t)sample * mc.num_chains_local + chain;
@@ -275,8 +289,10 @@ k_mc_rbm_block(const RbmDev psi, const cplx* __restrict__ Wp, const McParams mc,
     auto re_log_psi = [&]() -> double {
         cplx p(0.0, 0.0);
         if(FW_REAL) {
+            double p1 = 0.0;
             #pragma unroll
-            for(int k = 0; k < K; k++) p.re += lc0_re_pq(th[k].re, th[k].im);
+            for(int k = 0; k < K; k++) { if(k & 1) lc0_re_pq_acc(th[k].re, th[k].im, p1); else lc0_re_pq_acc(th[k].re, th[k].im, p.re); }
+            p.re += p1;
         } else {
             #pragma unroll
             for(int k = 0; k < K; k++) p += lc0_pq(th[k].re, th[k].im);
