@@ -292,10 +292,8 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 }
 __device__ __forceinline__ double bit_sign(const uint64_t* cw, unsigned i) { return ((cw[i >> 6] >> (i & 63u)) & 1ull) ? 1.0 : -1.0; }
 
-constexpr int RD_KC = 32, RD_CB = 128, RD_PAD = 8;                    // 8 samples per warp, 128 real columns per pass
-constexpr int RD_STRIDE = RD_CB + RD_PAD;
-constexpr int RD_STAGE_DOUBLES = RD_KC * RD_STRIDE;
-constexpr size_t RD_SMEM = 2 * RD_STAGE_DOUBLES * sizeof(double);       // double-buffered V tile (cp.async)
+constexpr int RD_KC = 32, RD_PAD = 8;                                  // 8 samples per warp, RD_CB real columns per pass
+constexpr size_t rd_smem(int cb) { return 2 * (size_t)RD_KC * (cb + RD_PAD) * sizeof(double); }   // double-buffered V tile (cp.async)
 
 __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool valid) {
     const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -305,10 +303,11 @@ __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsr
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template<int N_> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
 
-template<int RW>                                          // warps per block: 8 samples each
+template<int RW, int RD_CB>                               // warps per block (8 samples each); real columns per pass (64 | 128)
 __global__ void __launch_bounds__(RW * 32) k_rowdot_dmma(const uint64_t* __restrict__ conf, const cplx* __restrict__ T,
         const cplx* __restrict__ v, size_t ns, unsigned N, unsigned M, unsigned words, cplx* __restrict__ a_out) {
-    extern __shared__ __align__(16) double rd_smem[];
+    extern __shared__ __align__(16) double rd_buf[];
+    constexpr int RD_STRIDE = RD_CB + RD_PAD, RD_STAGE_DOUBLES = RD_KC * RD_STRIDE;
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u, row = lane >> 2, kq = lane & 3u;
     const size_t s = (size_t)blockIdx.x * (RW * 8) + warp * 8u + row;          // this lane's sample (A row / C row)
     uint64_t cw[MAXW] = {0ull, 0ull, 0ull, 0ull};
@@ -319,7 +318,7 @@ __global__ void __launch_bounds__(RW * 32) k_rowdot_dmma(const uint64_t* __restr
     const unsigned nkc = (N + RD_KC - 1) / RD_KC, ncb = (ncol + RD_CB - 1) / RD_CB, nstage = nkc * ncb;
     // stage q = (column block q / nkc, site chunk q % nkc): 32 sites x 128 doubles, 16-byte cp.async chunks, zero-filled OOB
     auto issue = [&](unsigned q) {
-        double* dst = rd_smem + (q & 1u) * RD_STAGE_DOUBLES;
+        double* dst = rd_buf + (q & 1u) * RD_STAGE_DOUBLES;
         const unsigned cb = (q / nkc) * RD_CB, i0 = (q % nkc) * RD_KC;
         for(unsigned e = threadIdx.x; e < RD_KC * (RD_CB / 2); e += RW * 32) {
             const unsigned kk = e / (RD_CB / 2), c = (e % (RD_CB / 2)) * 2u;
@@ -336,7 +335,7 @@ __global__ void __launch_bounds__(RW * 32) k_rowdot_dmma(const uint64_t* __restr
     for(unsigned q = 0; q < nstage; q++) {
         if(q + 1u < nstage) { issue(q + 1u); cp_async_wait<1>(); } else cp_async_wait<0>();
         __syncthreads();
-        const double* Vs = rd_smem + (q & 1u) * RD_STAGE_DOUBLES;
+        const double* Vs = rd_buf + (q & 1u) * RD_STAGE_DOUBLES;
         const unsigned cb = (q / nkc) * RD_CB, i0 = (q % nkc) * RD_KC;
         #pragma unroll 2
         for(unsigned k4 = 0; k4 < RD_KC / 4; k4++) {
@@ -1158,13 +1157,22 @@ void TDVP::rowdot(const cplx* v_dev) {
     if(factorised && use_dmma()) {
         static bool attr_set = false;
         if(!attr_set) {
-            ANGPU_CUDA(cudaFuncSetAttribute(k_rowdot_dmma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RD_SMEM));
-            ANGPU_CUDA(cudaFuncSetAttribute(k_rowdot_dmma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RD_SMEM));
+            ANGPU_CUDA(cudaFuncSetAttribute(k_rowdot_dmma<8, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rd_smem(128)));
+            ANGPU_CUDA(cudaFuncSetAttribute(k_rowdot_dmma<4, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rd_smem(128)));
+            ANGPU_CUDA(cudaFuncSetAttribute(k_rowdot_dmma<8, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rd_smem(64)));
+            ANGPU_CUDA(cudaFuncSetAttribute(k_rowdot_dmma<4, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rd_smem(64)));
             attr_set = true;
         }
-        // 64 samples per block, or 32 when that would leave SMs without a block (C2: 8192 samples -> 256 blocks, not 128)
-        if(ns >= (size_t)ctx().num_sms * 2 * 64) k_rowdot_dmma<8><<<ceil_div(ns, 64), 256, RD_SMEM, stream()>>>(S.conf.p, T.p, v_dev, ns, rbm_N, rbm_M, words, row_a.p);
-        else k_rowdot_dmma<4><<<ceil_div(ns, 32), 128, RD_SMEM, stream()>>>(S.conf.p, T.p, v_dev, ns, rbm_N, rbm_M, words, row_a.p);
+        // 64 samples per block, or 32 when that would leave SMs without a block (C2: 8192 samples -> 256 blocks, not 128);
+        // 128 real columns per pass for N <= 64 (C2), 64 (86 registers, more resident blocks) for wider lattices (C5: -6 %)
+        const bool big = ns >= (size_t)ctx().num_sms * 2 * 64;
+        if(rbm_N <= 64u) {
+            if(big) k_rowdot_dmma<8, 128><<<ceil_div(ns, 64), 256, rd_smem(128), stream()>>>(S.conf.p, T.p, v_dev, ns, rbm_N, rbm_M, words, row_a.p);
+            else k_rowdot_dmma<4, 128><<<ceil_div(ns, 32), 128, rd_smem(128), stream()>>>(S.conf.p, T.p, v_dev, ns, rbm_N, rbm_M, words, row_a.p);
+        } else {
+            if(big) k_rowdot_dmma<8, 64><<<ceil_div(ns, 64), 256, rd_smem(64), stream()>>>(S.conf.p, T.p, v_dev, ns, rbm_N, rbm_M, words, row_a.p);
+            else k_rowdot_dmma<4, 64><<<ceil_div(ns, 32), 128, rd_smem(64), stream()>>>(S.conf.p, T.p, v_dev, ns, rbm_N, rbm_M, words, row_a.p);
+        }
     }
     else if(factorised) k_rowdot_rbm<<<ceil_div(ns, RBM_ST), 256, 0, stream()>>>(S.conf.p, T.p, v_dev, ns, rbm_N, rbm_M, words, row_a.p);
     else k_rowdot_dense<<<(unsigned)ns, 256, 0, stream()>>>(O.p, v_dev, P, row_a.p);
