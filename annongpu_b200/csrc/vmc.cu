@@ -514,7 +514,7 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_colreduce_dmma(const uint64_t
             const bool live = sb + st < s1;
             #pragma unroll
             for(int q = 0; q < ITW; q++) {
-                const unsigned it = warp + (unsigned)q * CD_WARPS;
+                const unsigned it = blockIdx.z * (CD_WARPS * ITW) + warp + (unsigned)q * CD_WARPS;
                 if(it < ntile_i) {                                 // warp-uniform
                     const unsigned i = it * 8u + row;
                     const double asg = (live && i < N) ? bit_sign(sconf[st], i) : 0.0;
@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(CD_WARPS * 32) k_colreduce_dmma(const uint64_t
     const size_t P = (size_t)N * M;
     #pragma unroll
     for(int q = 0; q < ITW; q++) {
-        const unsigned it = warp + (unsigned)q * CD_WARPS;
+        const unsigned it = blockIdx.z * (CD_WARPS * ITW) + warp + (unsigned)q * CD_WARPS;
         if(it < ntile_i) {
             const unsigned i = it * 8u + row;
             #pragma unroll
@@ -1004,7 +1004,12 @@ static ColPartials col_reduce_partials(TDVP& t, const cplx* X, bool want_mean) {
             const dim3 g128(ceil_div(2 * t.rbm_M, 128), chunks), g64(ceil_div(2 * t.rbm_M, 64), chunks);
             if(t.rbm_N <= 64u) k_colreduce_dmma<1, 64><<<g64, CD_WARPS * 32, 0, stream()>>>(t.S.conf.p, t.T.p, t.S.weight.p, X, ns, t.rbm_N, t.rbm_M, t.words, chunk, px);
             else if(t.rbm_N <= 128u) k_colreduce_dmma<2, 64><<<g64, CD_WARPS * 32, 0, stream()>>>(t.S.conf.p, t.T.p, t.S.weight.p, X, ns, t.rbm_N, t.rbm_M, t.words, chunk, px);
-            else k_colreduce_dmma<4, 64><<<g64, CD_WARPS * 32, 0, stream()>>>(t.S.conf.p, t.T.p, t.S.weight.p, X, ns, t.rbm_N, t.rbm_M, t.words, chunk, px);
+            else {
+                // wider lattices: 16 site tiles (128 sites) per block along grid.z instead of 4 tiles per warp in one block
+                // (183 registers, one block per SM): C5 (N = 200) runs 2 z-slices of the <2,64> build
+                const dim3 g64z(g64.x, g64.y, ceil_div((t.rbm_N + 7u) / 8u, CD_WARPS * 2));
+                k_colreduce_dmma<2, 64><<<g64z, CD_WARPS * 32, 0, stream()>>>(t.S.conf.p, t.T.p, t.S.weight.p, X, ns, t.rbm_N, t.rbm_M, t.words, chunk, px);
+            }
         }
         else k_col_reduce_rbm<false><<<dim3(jb, ib, chunks), 128, 0, stream()>>>(t.S.conf.p, t.T.p, t.S.weight.p, X, ns, t.rbm_N, t.rbm_M, t.words, chunk, pm, px);
         ANGPU_CHECK_LAUNCH(); count_launch();
