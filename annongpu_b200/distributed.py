@@ -34,8 +34,18 @@ def shard_range(total, rank, world):
     return begin, total * (rank + 1) // world - begin
 
 
+_views = {}
+
+
 def allreduce_hook(ptr, count):
-    t = torch.as_tensor(_DevArray(ptr, count), device=torch.device("cuda", torch.cuda.current_device()))
+    # the library reduces a handful of grow-only buffers over and over (packed sums, one P-vector per CG product): the
+    # zero-copy tensor views are cached by (pointer, count) so that a call costs one dict lookup + dist.all_reduce
+    t = _views.get((ptr, count))
+    if t is None:
+        if len(_views) >= 64:
+            _views.clear()
+        t = torch.as_tensor(_DevArray(ptr, count), device=torch.device("cuda", torch.cuda.current_device()))
+        _views[(ptr, count)] = t
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
 
 
@@ -63,6 +73,7 @@ def init_from_env(backend="nccl"):
 
 
 def shutdown():
+    _views.clear()
     api.set_allreduce(None)
     api.synchronize()
     api.set_stream(None)
