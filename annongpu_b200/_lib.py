@@ -23,7 +23,7 @@ if not os.path.exists(LIB_PATH):
 lib = C.CDLL(LIB_PATH)
 
 vp, u32, u64, ull, dbl, i32 = C.c_void_p, C.c_uint, C.c_uint64, C.c_ulonglong, C.c_double, C.c_int
-ALLREDUCE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_ulonglong, C.c_void_p)
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_ulonglong, C.c_void_p)
 
 _SIGNATURES = {
     "angpu_init": [i32],
@@ -32,6 +32,10 @@ _SIGNATURES = {
     "angpu_profiler_start": [],
     "angpu_profiler_stop": [],
     "angpu_set_allreduce": [ALLREDUCE_FN, vp],
+    "angpu_comm_unique_id": [vp],
+    "angpu_comm_init": [vp, i32, i32],
+    "angpu_comm_destroy": [],
+    "angpu_comm_rank": [vp, vp],
     "angpu_spins_enumerate": [u64, u32, vp],
     "angpu_pauli_apply": [vp, vp, vp, u32, vp, vp],
     "angpu_activation": [vp, u32, vp, vp],
@@ -59,6 +63,9 @@ _SIGNATURES = {
     "angpu_ensemble_local_steps": [vp, vp],
     "angpu_ensemble_set_shard": [vp, u32, u32],
     "angpu_mc_acceptance": [vp, vp],
+    "angpu_mc_counters": [vp, vp],
+    "angpu_mc_get_call_index": [vp, vp],
+    "angpu_mc_set_call_index": [vp, u32],
     "angpu_ensemble_sample": [vp, vp, vp, vp],
     "angpu_log_psi_s": [vp, vp, vp],
     "angpu_psi_O_k": [vp, vp, vp],
@@ -104,6 +111,7 @@ _SIGNATURES = {
     "angpu_tdvp_S_dot_vector": [vp, vp, vp],
     "angpu_tdvp_solve_cg": [vp, dbl, u32, dbl, dbl, vp, vp, vp, vp],
     "angpu_tdvp_solve_dense": [vp, dbl, dbl, vp, vp],
+    "angpu_tdvp_apply_update": [vp, vp, vp],
     "angpu_tdvp_build_S_tensorcore": [vp],
     "angpu_tdvp_set_profile": [vp, i32],
     "angpu_tdvp_phase_ms": [vp, vp],
@@ -122,9 +130,19 @@ lib.angpu_launch_count.argtypes = [i32]
 EXPORTED = sorted(list(_SIGNATURES) + ["angpu_last_error", "angpu_launch_count"])
 
 
+# an exception raised inside the Python all-reduce callback cannot cross the C frames: the trampoline (api.set_allreduce)
+# parks it here and returns non-zero, the failing entry point returns an error, and check() re-raises the original
+pending_callback_error = []
+
+
 def check(status):
     if status != 0:
-        raise AngpuError(lib.angpu_last_error().decode("utf-8", "replace"))
+        msg = lib.angpu_last_error().decode("utf-8", "replace")
+        if pending_callback_error:
+            exc = pending_callback_error.pop()
+            pending_callback_error.clear()
+            raise AngpuError(msg) from exc
+        raise AngpuError(msg)
 
 
 def call(name, *args):

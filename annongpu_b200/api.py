@@ -20,6 +20,7 @@ import ctypes as C
 
 import numpy as np
 
+from . import _lib
 from ._lib import call, lib, ALLREDUCE_FN
 from .factories import PauliSum, masks_to_words, words_for
 
@@ -29,8 +30,10 @@ __all__ = [
     "HilbertSpaceDistance", "KullbackLeibler",
     "log_psi_s", "psi_O_k", "psi_O_k_vector", "log_psi", "psi_vector", "log_psi_vector", "apply_operator",
     "local_energies", "activation_function", "pauli_apply", "setDevice", "start_profiling", "stop_profiling",
-    "synchronize", "launch_count", "set_stream", "measure_fp64_tflops",
+    "synchronize", "launch_count", "set_stream", "measure_fp64_tflops", "AngpuError",
+    "comm_unique_id", "comm_init", "comm_destroy", "comm_rank",
 ]
+AngpuError = _lib.AngpuError
 
 
 def _c128(x):
@@ -606,6 +609,25 @@ class MonteCarloSpins(_Ensemble):
         a, r = self.acceptances
         return float(a) / float(a + r) if a + r else float("nan")
 
+    @property
+    def call_index(self):
+        """Number of sampling calls made so far = position of the random streams (they continue across calls)."""
+        n = C.c_uint()
+        call("angpu_mc_get_call_index", self._h, C.byref(n))
+        return int(n.value)
+
+    @call_index.setter
+    def call_index(self, value):
+        call("angpu_mc_set_call_index", self._h, int(value))
+
+    @property
+    def exact_decisions(self):
+        """Proposals of the last call whose accept/reject decision needed the fp64 evaluation (fp32-screened PsiRBM
+        sampler; 0 for the all-fp64 samplers).  No reference counterpart."""
+        out = np.zeros(4, dtype=np.uint64)
+        call("angpu_mc_counters", self._h, _p(out))
+        return int(out[2])
+
 
 # -------------------------------------------------------------------------------------------- functionals
 
@@ -865,13 +887,18 @@ class TDVP:
         return dict(sample=float(out[0]), eloc=float(out[1]), ok_reduce=float(out[2]), total=float(out[3]),
                     s_build=float(out[4]), solve=float(out[5]))
 
-    def solve_cg(self, tol=1e-6, max_iter=1000, shift_abs=0.0, shift_rel=1e-3, rhs_phase=1.0):
-        """NEW: matrix-free CG for (S + shift_abs I + shift_rel diag S) x = rhs_phase F. Returns (x, iterations, rel_residual)."""
-        x = np.empty(self.num_params, dtype=np.complex128)
+    def solve_cg(self, tol=1e-6, max_iter=1000, shift_abs=0.0, shift_rel=1e-3, rhs_phase=1.0, keep_on_device=False):
+        """NEW: matrix-free CG for (S + shift_abs I + shift_rel diag S) x = rhs_phase F. Returns (x, iterations, rel_residual);
+        with keep_on_device the solution is not copied out (x is None) -- follow up with apply_update."""
+        x = None if keep_on_device else np.empty(self.num_params, dtype=np.complex128)
         it, rr = C.c_uint(), C.c_double()
         call("angpu_tdvp_solve_cg", self._h, float(tol), int(max_iter), float(shift_abs), float(shift_rel),
-             _p(_pair(rhs_phase)), _p(x), C.byref(it), C.byref(rr))
+             _p(_pair(rhs_phase)), None if x is None else _p(x), C.byref(it), C.byref(rr))
         return x, int(it.value), float(rr.value)
+
+    def apply_update(self, psi, alpha):
+        """NEW: psi.params += alpha * x for the x of the last solve, on the device (the SR / TDVP parameter step)."""
+        call("angpu_tdvp_apply_update", self._h, psi._h, _p(_pair(alpha)))
 
     def solve(self, shift_abs=0.0, shift_rel=1e-3, rhs_phase=1.0):
         """NEW: dense Cholesky solve of the same system (needs eval, i.e. a dense S)."""
@@ -945,5 +972,38 @@ def set_allreduce(fn):
         _allreduce_cb = None
         lib.angpu_set_allreduce(C.cast(None, ALLREDUCE_FN), None)
         return
-    _allreduce_cb = ALLREDUCE_FN(lambda ptr, count, user: fn(int(ptr), int(count)))
+    def trampoline(ptr, count, user):
+        # ctypes would print and swallow an exception raised here, and the library would go on with un-reduced partial
+        # sums: park it, report failure to C (the entry point then fails) and let _lib.check() re-raise it
+        try:
+            fn(int(ptr), int(count))
+            return 0
+        except BaseException as exc:                 # noqa: BLE001  (must not propagate into the C frames)
+            _lib.pending_callback_error.append(exc)
+            return 1
+
+    _allreduce_cb = ALLREDUCE_FN(trampoline)
     lib.angpu_set_allreduce(_allreduce_cb, None)
+
+
+def comm_unique_id():
+    """128-byte NCCL unique id (rank 0 creates it, every rank passes it to comm_init)."""
+    buf = (C.c_ubyte * 128)()
+    call("angpu_comm_unique_id", buf)
+    return bytes(buf)
+
+
+def comm_init(unique_id, rank, world):
+    """Creates the library's own NCCL communicator on the current device; ensembles created afterwards are sharded."""
+    buf = (C.c_ubyte * 128).from_buffer_copy(bytes(unique_id))
+    call("angpu_comm_init", buf, int(rank), int(world))
+
+
+def comm_destroy():
+    call("angpu_comm_destroy")
+
+
+def comm_rank():
+    r, w = C.c_int(), C.c_int()
+    call("angpu_comm_rank", C.byref(r), C.byref(w))
+    return r.value, w.value

@@ -62,6 +62,10 @@ int angpu_profiler_start(void) { API_BEGIN ANGPU_CUDA(cudaProfilerStart()); API_
 int angpu_profiler_stop(void) { API_BEGIN ANGPU_CUDA(cudaProfilerStop()); API_END }
 unsigned long long angpu_launch_count(int reset) { const unsigned long long n = ctx().launches; if(reset) ctx().launches = 0; return n; }
 int angpu_set_allreduce(angpu_allreduce_fn fn, void* user) { set_allreduce(fn, user); return 0; }
+int angpu_comm_unique_id(unsigned char id_out[ANGPU_COMM_ID_BYTES]) { API_BEGIN NOTNULL(id_out); comm_unique_id(id_out); API_END }
+int angpu_comm_init(const unsigned char id[ANGPU_COMM_ID_BYTES], int rank, int world) { API_BEGIN NOTNULL(id); comm_init(id, rank, world); API_END }
+int angpu_comm_destroy(void) { API_BEGIN comm_destroy(); API_END }
+int angpu_comm_rank(int* rank_out, int* world_out) { API_BEGIN NOTNULL(rank_out); NOTNULL(world_out); *rank_out = comm_rank(); *world_out = comm_world(); API_END }
 
 // ---- primitives
 int angpu_spins_enumerate(uint64_t index, unsigned words, uint64_t* conf_out) {
@@ -181,6 +185,14 @@ int angpu_ensemble_set_shard(angpu_ensemble_t ens, unsigned rank, unsigned world
     API_END
 }
 int angpu_mc_acceptance(angpu_ensemble_t ens, unsigned long long out[2]) { API_BEGIN NOTNULL(ens); NOTNULL(out); ens->e.acceptance(out); API_END }
+int angpu_mc_get_call_index(angpu_ensemble_t ens, unsigned* out) { API_BEGIN NOTNULL(ens); NOTNULL(out); *out = ens->e.call; API_END }
+int angpu_mc_set_call_index(angpu_ensemble_t ens, unsigned call_index) { API_BEGIN NOTNULL(ens); ens->e.call = call_index; API_END }
+int angpu_mc_counters(angpu_ensemble_t ens, unsigned long long out[4]) {
+    API_BEGIN NOTNULL(ens); NOTNULL(out);
+    out[0] = out[1] = out[2] = out[3] = 0;
+    if(ens->e.d_acc_rej.n >= 4) ens->e.d_acc_rej.download(out, 4);
+    API_END
+}
 int angpu_ensemble_sample(angpu_ensemble_t ens, angpu_psi_t psi, uint64_t* confs_out, double* log_psi_out) {
     API_BEGIN NOTNULL(ens); NOTNULL(psi);
     SampleSet S;
@@ -355,7 +367,7 @@ int angpu_tdvp_get_E_local_samples(angpu_tdvp_t tdvp, double* out) { API_BEGIN N
 int angpu_tdvp_S_dot_vector(angpu_tdvp_t tdvp, const double* vec, double* out) { API_BEGIN NOTNULL(tdvp); NOTNULL(vec); NOTNULL(out); tdvp->t->S_dot_vector(cp(vec), cp(out)); API_END }
 int angpu_tdvp_solve_cg(angpu_tdvp_t tdvp, double tol, unsigned max_iter, double shift_abs, double shift_rel, const double rhs_phase[2],
                         double* x_out, unsigned* iterations_out, double* rel_residual_out) {
-    API_BEGIN NOTNULL(tdvp); NOTNULL(rhs_phase); NOTNULL(x_out);
+    API_BEGIN NOTNULL(tdvp); NOTNULL(rhs_phase);
     double rr = 0.0;
     const int it = tdvp->t->solve_cg(tol, max_iter, shift_abs, shift_rel, c2(rhs_phase), cp(x_out), &rr);
     if(iterations_out) *iterations_out = (unsigned)it;
@@ -367,7 +379,14 @@ int angpu_tdvp_set_profile(angpu_tdvp_t tdvp, int enable) { API_BEGIN NOTNULL(td
 int angpu_tdvp_phase_ms(angpu_tdvp_t tdvp, double out[6]) { API_BEGIN NOTNULL(tdvp); NOTNULL(out); for(int i = 0; i < 6; i++) out[i] = tdvp->t->phase_ms[i]; API_END }
 int angpu_measure_fp64_tflops(double* out) { API_BEGIN NOTNULL(out); *out = measure_fp64_tflops(); API_END }
 int angpu_tdvp_solve_dense(angpu_tdvp_t tdvp, double shift_abs, double shift_rel, const double rhs_phase[2], double* x_out) {
-    API_BEGIN NOTNULL(tdvp); NOTNULL(rhs_phase); NOTNULL(x_out); tdvp->t->solve_dense(shift_abs, shift_rel, c2(rhs_phase), cp(x_out)); API_END
+    API_BEGIN NOTNULL(tdvp); NOTNULL(rhs_phase); tdvp->t->solve_dense(shift_abs, shift_rel, c2(rhs_phase), cp(x_out)); API_END
+}
+int angpu_tdvp_apply_update(angpu_tdvp_t tdvp, angpu_psi_t psi, const double alpha[2]) {
+    API_BEGIN NOTNULL(tdvp); NOTNULL(psi); NOTNULL(alpha);
+    ANGPU_REQUIRE(tdvp->t->last_x != nullptr, "TDVP: no solution on the device (call solve_cg / solve_dense first)");
+    ANGPU_REQUIRE(psi->p->P == tdvp->t->P, "TDVP: num_params differs from psi's");
+    psi->p->add_params_dev(tdvp->t->last_x, c2(alpha));
+    API_END
 }
 
 #pragma GCC visibility pop

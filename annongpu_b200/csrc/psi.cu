@@ -1,6 +1,7 @@
 // Host-side wavefunction objects: parameter bookkeeping + kernel launches.
 #include "psi.hpp"
 #include "rbm_kernels.cuh"
+#include "rbm_sampler.cuh"
 #include "deep_kernels.cuh"
 #include "cnn_kernels.cuh"
 #include <algorithm>
@@ -91,7 +92,44 @@ void generic_mc(const Dev& d, const McParams& mc, SampleSet& S, unsigned long lo
 
 } // namespace
 
+void Psi::add_params_dev(const cplx* x_dev, cplx alpha) {
+    std::vector<cplx> x(P), p(P);
+    ANGPU_CUDA(cudaMemcpyAsync(x.data(), x_dev, sizeof(cplx) * P, cudaMemcpyDeviceToHost, stream()));
+    ANGPU_CUDA(cudaStreamSynchronize(stream()));
+    get_params(p.data());
+    for(unsigned k = 0; k < P; k++) p[k] += alpha * x[k];
+    set_params(p.data());
+}
+
 // ---------------------------------------------------------------------------------------- PsiRBM
+
+// W += alpha x on every device copy of the weights: W itself, the row-padded copy and the fp32 copy of the screened sampler
+__global__ void k_rbm_add_params(cplx* __restrict__ W, cplx* __restrict__ Wpad, float4* __restrict__ Wf, const cplx* __restrict__ x,
+                                 cplx alpha, unsigned N, unsigned M, unsigned Mpad, unsigned KK) {
+    for(size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < (size_t)N * M; k += (size_t)gridDim.x * blockDim.x) {
+        const unsigned i = (unsigned)(k / M), j = (unsigned)(k - (size_t)i * M);
+        cplx w = W[k];
+        cfma(w, alpha, x[k]);
+        W[k] = w;
+        if(Wpad) Wpad[(size_t)i * Mpad + j] = w;
+        if(Wf) {
+            float* f = reinterpret_cast<float*>(&Wf[((size_t)i * KK + (j >> 6)) * 32u + ((j & 63u) >> 1)]);
+            f[j & 1u] = (float)w.re; f[2u + (j & 1u)] = (float)w.im;
+        }
+    }
+}
+void PsiRBM::add_params_dev(const cplx* x_dev, cplx alpha) {
+    const unsigned grid = (unsigned)std::min<size_t>(((size_t)P + 255) / 256, (size_t)ctx().num_sms * 16);
+    k_rbm_add_params<<<grid, 256, 0, stream()>>>(dW.p, Mpad != M && Mpad ? dWpad.p : nullptr, dWf.n ? dWf.p : nullptr, x_dev, alpha, N, M, Mpad,
+                                                 M <= 512u ? rbm_sampler_KK(M) : 0u);
+    ANGPU_CHECK_LAUNCH(); count_launch();
+    host_stale = true;
+}
+void PsiRBM::sync_host() const {
+    if(!host_stale) return;
+    dW.download(hW.data(), hW.size());
+    host_stale = false;
+}
 
 PsiRBM::PsiRBM(unsigned N_, unsigned M_, const cplx* W, cplx fw_, cplx lp_) {
     kind = RBM; N = N_; M = M_; words = words_for(N); P = N * M; lp = lp_; fw = fw_;
@@ -106,12 +144,25 @@ void PsiRBM::upload() {
     // (rbm_kernels.cuh); when M already is such a multiple (C2: 256) the samplers read W itself
     Mpad = 0;
     if(M <= 2048u) {
-        Mpad = (M <= 512u) ? 32u * (M <= 32u ? 1u : M <= 64u ? 2u : M <= 128u ? 4u : M <= 256u ? 8u : 16u)
-                           : (unsigned)MC_BLOCK_T * ((M + MC_BLOCK_T - 1) / MC_BLOCK_T);
+        Mpad = (M <= 512u) ? 64u * rbm_sampler_KK(M) : (unsigned)MC_BLOCK_T * ((M + MC_BLOCK_T - 1) / MC_BLOCK_T);
         if(Mpad != M) {
             std::vector<cplx> wp((size_t)N * Mpad, cplx(0.0, 0.0));
             for(unsigned i = 0; i < N; i++) std::memcpy(&wp[(size_t)i * Mpad], &hW[(size_t)i * M], sizeof(cplx) * M);
             dWpad.upload(wp);
+        }
+        if(M <= 512u) {
+            // fp32 copy for the screened sampler (rbm_sampler.cuh): float4 (Re W_pj0, Re W_pj1, Im W_pj0, Im W_pj1) at
+            // [(p KK + kk) 32 + lane], j0 = 64 kk + 2 lane, zeros beyond M
+            const unsigned KK = rbm_sampler_KK(M);
+            std::vector<float4> wf((size_t)N * KK * 32u);
+            for(unsigned i = 0; i < N; i++)
+                for(unsigned kk = 0; kk < KK; kk++)
+                    for(unsigned l = 0; l < 32u; l++) {
+                        const unsigned j0 = 64u * kk + 2u * l;
+                        const cplx a = j0 < M ? hW[(size_t)i * M + j0] : cplx(0.0, 0.0), b = j0 + 1u < M ? hW[(size_t)i * M + j0 + 1u] : cplx(0.0, 0.0);
+                        wf[((size_t)i * KK + kk) * 32u + l] = make_float4((float)a.re, (float)b.re, (float)a.im, (float)b.im);
+                    }
+            dWf.upload(wf);
         }
     }
 }
@@ -191,42 +242,59 @@ void PsiRBM::ok_rows(SampleSet& S, size_t s0, size_t cnt, cplx* out) {
 template<int K, int WORDS>
 static void launch_mc_rbm(const RbmDev& d, const cplx* Wp, const McParams& mc, SampleSet& S, unsigned long long* acc_rej_dev) {
     const unsigned wpb = MC_RBM_THREADS / 32, grid = ceil_div(mc.num_chains_local, wpb);
-    // resident blocks per SM requested from ptxas: 8 (<= 128 registers); for K = 8 with one-word configurations (the C2
-    // shape) 10 blocks = 20 warps per SM fit in 96 registers now that the W row is re-read on rejection instead of being
-    // kept live (1.79 -> 1.77 ms per 8192 chains, and 2.77 instead of 3.46 waves).  ANGPU_MC_MINB=8 selects the 8-block build.
-    static const int minb = [] { const char* e = getenv("ANGPU_MC_MINB"); return e ? atoi(e) : 10; }();
-    constexpr int DEF = (K <= 8) ? 8 : 1;
-    if(K == 8 && WORDS == 1 && minb == 10) {
-        if(d.fw.im == 0.0) k_mc_rbm<K, WORDS, true, (K == 8 && WORDS == 1) ? 10 : DEF><<<grid, wpb * 32, 0, stream()>>>(d, Wp, mc, S.conf.p, S.log_psi.p, S.angles.p, acc_rej_dev);
-        else k_mc_rbm<K, WORDS, false, (K == 8 && WORDS == 1) ? 10 : DEF><<<grid, wpb * 32, 0, stream()>>>(d, Wp, mc, S.conf.p, S.log_psi.p, S.angles.p, acc_rej_dev);
-    } else if(d.fw.im == 0.0)
-        k_mc_rbm<K, WORDS, true, DEF><<<grid, wpb * 32, 0, stream()>>>(d, Wp, mc, S.conf.p, S.log_psi.p, S.angles.p, acc_rej_dev);
-    else
-        k_mc_rbm<K, WORDS, false, DEF><<<grid, wpb * 32, 0, stream()>>>(d, Wp, mc, S.conf.p, S.log_psi.p, S.angles.p, acc_rej_dev);
+    // the fp64 sampler (complex final weight, or ANGPU_MC_SCREEN=0): resident blocks per SM requested from ptxas: 8
+    // (<= 128 registers); for K = 8 with one-word configurations 10 blocks = 20 warps per SM fit in 96 registers
+    constexpr int MINB = (K == 8 && WORDS == 1) ? 10 : (K <= 8) ? 8 : 1;
+    if(d.fw.im == 0.0) k_mc_rbm<K, WORDS, true, MINB><<<grid, wpb * 32, 0, stream()>>>(d, Wp, mc, S.conf.p, S.log_psi.p, S.angles.p, acc_rej_dev);
+    else k_mc_rbm<K, WORDS, false, MINB><<<grid, wpb * 32, 0, stream()>>>(d, Wp, mc, S.conf.p, S.log_psi.p, S.angles.p, acc_rej_dev);
     ANGPU_CHECK_LAUNCH(); count_launch();
 }
-template<int K>
-static void launch_mc_rbm_k(const RbmDev& d, const cplx* Wp, const McParams& mc, SampleSet& S, unsigned long long* a) {
+// the fp32-screened sampler (rbm_sampler.cuh): real final weight
+template<int KK, int WORDS>
+static void launch_mc_rbm_scr(const RbmDev& d, const cplx* Wp, const float4* Wf, const McParams& mc, SampleSet& S, unsigned long long* stats) {
+    const unsigned wpb = MC_RBM_THREADS / 32, grid = ceil_div(mc.num_chains_local, wpb);
+    static const int refresh = [] { const char* e = getenv("ANGPU_MC_REFRESH"); return e ? atoi(e) : 16; }();   // 16 or 32 accepted flips between syncs
+    static const int minb = [] { const char* e = getenv("ANGPU_MC_MINB"); return e ? atoi(e) : 8; }();
+    auto go = [&](auto kern) { kern<<<grid, wpb * 32, 0, stream()>>>(d, Wp, Wf, mc, S.conf.p, S.log_psi.p, S.angles.p, stats); };
+    if(KK <= 4 && minb >= 10) { if(refresh >= 32) go(k_mc_rbm_scr<KK, WORDS, (KK <= 4) ? 10 : 4, 32>); else go(k_mc_rbm_scr<KK, WORDS, (KK <= 4) ? 10 : 4, 16>); }
+    else { if(refresh >= 32) go(k_mc_rbm_scr<KK, WORDS, (KK <= 4) ? 8 : 4, 32>); else go(k_mc_rbm_scr<KK, WORDS, (KK <= 4) ? 8 : 4, 16>); }
+    ANGPU_CHECK_LAUNCH(); count_launch();
+}
+template<int KK>
+static void launch_mc_rbm_kk(const RbmDev& d, const cplx* Wp, const float4* Wf, bool screened, const McParams& mc, SampleSet& S, unsigned long long* a) {
+    if(screened) {
+        switch(d.words) {
+            case 1: launch_mc_rbm_scr<KK, 1>(d, Wp, Wf, mc, S, a); break;
+            case 2: launch_mc_rbm_scr<KK, 2>(d, Wp, Wf, mc, S, a); break;
+            case 3: launch_mc_rbm_scr<KK, 3>(d, Wp, Wf, mc, S, a); break;
+            default: launch_mc_rbm_scr<KK, 4>(d, Wp, Wf, mc, S, a); break;
+        }
+        return;
+    }
     switch(d.words) {
-        case 1: launch_mc_rbm<K, 1>(d, Wp, mc, S, a); break;
-        case 2: launch_mc_rbm<K, 2>(d, Wp, mc, S, a); break;
-        case 3: launch_mc_rbm<K, 3>(d, Wp, mc, S, a); break;
-        default: launch_mc_rbm<K, 4>(d, Wp, mc, S, a); break;
+        case 1: launch_mc_rbm<2 * KK, 1>(d, Wp, mc, S, a); break;
+        case 2: launch_mc_rbm<2 * KK, 2>(d, Wp, mc, S, a); break;
+        case 3: launch_mc_rbm<2 * KK, 3>(d, Wp, mc, S, a); break;
+        default: launch_mc_rbm<2 * KK, 4>(d, Wp, mc, S, a); break;
     }
 }
-static unsigned rbm_sampler_K(unsigned M) { return M <= 32u ? 1u : M <= 64u ? 2u : M <= 128u ? 4u : M <= 256u ? 8u : 16u; }
 
 void PsiRBM::mc_sample(const McParams& mc, SampleSet& S, unsigned long long* acc_rej_dev) {
     if(mc.num_chains_local == 0) return;
     const RbmDev d = dev();
     if(M <= 512u) {
         S.angles.resize(S.ns * M);
-        switch(rbm_sampler_K(M)) {
-            case 1: launch_mc_rbm_k<1>(d, Wpad(), mc, S, acc_rej_dev); break;
-            case 2: launch_mc_rbm_k<2>(d, Wpad(), mc, S, acc_rej_dev); break;
-            case 4: launch_mc_rbm_k<4>(d, Wpad(), mc, S, acc_rej_dev); break;
-            case 8: launch_mc_rbm_k<8>(d, Wpad(), mc, S, acc_rej_dev); break;
-            default: launch_mc_rbm_k<16>(d, Wpad(), mc, S, acc_rej_dev); break;
+        // ANGPU_MC_SCREEN=1 selects the fp32-screened sampler (rbm_sampler.cuh): identical chains, but measured SLOWER than
+        // the all-fp64 sampler on B200 (C2: 2.3 vs 1.75 ms; FP32 runs at only 2x the FP64 rate, F2F at a quarter of it, and
+        // the kernel is issue-bound -- DESIGN.md 9.1), so it is opt-in
+        static const bool screen_on = [] { const char* e = getenv("ANGPU_MC_SCREEN"); return e && atoi(e) != 0; }();
+        const unsigned long long steps = (unsigned long long)N * ((unsigned long long)mc.num_therm + (unsigned long long)mc.num_sweeps * mc.steps_per_chain);
+        const bool screened = screen_on && fw.im == 0.0 && steps < 0xffffffffull;
+        switch(rbm_sampler_KK(M)) {
+            case 1: launch_mc_rbm_kk<1>(d, Wpad(), dWf.p, screened, mc, S, acc_rej_dev); break;
+            case 2: launch_mc_rbm_kk<2>(d, Wpad(), dWf.p, screened, mc, S, acc_rej_dev); break;
+            case 4: launch_mc_rbm_kk<4>(d, Wpad(), dWf.p, screened, mc, S, acc_rej_dev); break;
+            default: launch_mc_rbm_kk<8>(d, Wpad(), dWf.p, screened, mc, S, acc_rej_dev); break;
         }
         S.has_angles = true;
     } else if(M <= 2048u) {

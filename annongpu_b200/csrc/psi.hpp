@@ -39,6 +39,8 @@ struct Psi {
     virtual void get_params(cplx* out) const = 0;
     virtual void set_params(const cplx* in) = 0;
     virtual void set_log_prefactor(cplx v) { lp = v; }
+    // params += alpha * x with x resident on the device (SR / TDVP update); the default goes through the host copy
+    virtual void add_params_dev(const cplx* x_dev, cplx alpha);
 
     // fills S.log_psi (and S.weight = exp(2 Re log psi) when es_weights) for S.conf
     virtual void log_psi(SampleSet& S, bool es_weights) = 0;
@@ -50,20 +52,28 @@ struct Psi {
     virtual void mc_sample(const McParams& mc, SampleSet& S, unsigned long long* acc_rej_dev) = 0;
 };
 
+// unit pairs per lane of the warp-per-chain RBM samplers (rows padded to 64 KK hidden units)
+inline unsigned rbm_sampler_KK(unsigned M) { return M <= 64u ? 1u : M <= 128u ? 2u : M <= 256u ? 4u : 8u; }
+
 struct PsiRBM : Psi {
     unsigned M = 0;
     cplx fw{1.0, 0.0};
-    std::vector<cplx> hW;
+    mutable std::vector<cplx> hW;
     DevBuf<cplx> dW, dWpad;
+    DevBuf<float4> dWf;                 // fp32 copy of W in the screened sampler's layout (rbm_sampler.cuh), M <= 512
     unsigned Mpad = 0;
     const cplx* Wpad() const { return Mpad == M ? dW.p : dWpad.p; }
 
     PsiRBM(unsigned N_, unsigned M_, const cplx* W, cplx fw_, cplx lp_);
-    RbmDev dev() const { return RbmDev{N, M, words, P, lp, fw, dW.p}; }
+    RbmDev dev() const { return RbmDev{N, M, words, P, lp, fw, dW.p, (float)(2.0 * fw.re)}; }
     void upload();
-    Psi* clone() const override { return new PsiRBM(N, M, hW.data(), fw, lp); }
-    void get_params(cplx* out) const override { std::memcpy(out, hW.data(), sizeof(cplx) * P); }
-    void set_params(const cplx* in) override { hW.assign(in, in + P); upload(); }
+    // the device copies are updated in place by add_params_dev; the host copy is refreshed lazily
+    mutable bool host_stale = false;
+    void sync_host() const;
+    Psi* clone() const override { sync_host(); return new PsiRBM(N, M, hW.data(), fw, lp); }
+    void get_params(cplx* out) const override { sync_host(); std::memcpy(out, hW.data(), sizeof(cplx) * P); }
+    void set_params(const cplx* in) override { hW.assign(in, in + P); host_stale = false; upload(); }
+    void add_params_dev(const cplx* x_dev, cplx alpha) override;
     void log_psi(SampleSet& S, bool es_weights) override;
     void eloc(const Operator& op, SampleSet& S) override;
     void ok_rows(SampleSet& S, size_t s0, size_t cnt, cplx* out) override;

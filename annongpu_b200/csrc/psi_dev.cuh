@@ -25,6 +25,7 @@ struct RbmDev {
     unsigned N, M, words, P;
     cplx     lp, fw;
     const cplx* W;     // [N][M]
+    float    c2fw;     // (float)(2 Re fw): scale of the fp32-screened acceptance test (rbm_sampler.cuh)
 
     __host__ __device__ unsigned payload_elems() const { return M; }
     __host__ __device__ unsigned block_scratch_bytes() const { return 0u; }

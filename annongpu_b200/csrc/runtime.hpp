@@ -39,9 +39,14 @@ struct DevBuf {
     // grow-only: contents are NOT preserved on growth
     void resize(size_t n_) {
         if(n_ > cap) {
-            if(p) { ANGPU_CUDA(cudaStreamSynchronize(stream())); cudaFree(p); p = nullptr; }
-            ANGPU_CUDA(cudaMalloc(&p, sizeof(T) * (n_ ? n_ : 1)));
-            cap = n_ ? n_ : 1;
+            if(p) { ANGPU_CUDA(cudaStreamSynchronize(stream())); cudaFree(p); p = nullptr; n = cap = 0; }
+            T* q = nullptr;
+            const cudaError_t e = cudaMalloc(&q, sizeof(T) * (n_ ? n_ : 1));
+            if(e != cudaSuccess) {
+                cudaGetLastError();                               // clear the (non-sticky) allocation error; the buffer stays empty
+                throw Error(std::string("cudaMalloc of ") + std::to_string(sizeof(T) * n_) + " bytes: " + cudaGetErrorString(e));
+            }
+            p = q; cap = n_ ? n_ : 1;
         }
         n = n_;
     }

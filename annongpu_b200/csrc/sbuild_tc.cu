@@ -320,6 +320,7 @@ static void make_map(CUtensorMap* m, float* plane, unsigned P, size_t Kpad) {
 // S = (1/1) sum_s conj(A_sr) A_sc on the tensor cores.  Single-process only in this round (the centred form needs the
 // global <O_k>, which eval() has already all-reduced; the partial S of each rank is all-reduced afterwards).
 void TDVP::build_S_tensorcore() {
+    set_reduce(sharded);
     ANGPU_REQUIRE(evaluated, "TDVP: call eval first");
     ensure_dense_O(last_psi);
     mark(5);

@@ -8,14 +8,6 @@
 
 namespace angpu {
 
-static allreduce_fn g_allreduce = nullptr;
-static void* g_allreduce_user = nullptr;
-void set_allreduce(allreduce_fn fn, void* user) { g_allreduce = fn; g_allreduce_user = user; }
-bool has_allreduce() { return g_allreduce != nullptr; }
-void allreduce_sum(double* dev_ptr, size_t count) {
-    if(g_allreduce && count) g_allreduce(dev_ptr, (unsigned long long)count, g_allreduce_user);
-}
-
 // ============================================================================================ small kernels
 
 __global__ void k_fill(double* p, double v, size_t n) {
@@ -856,6 +848,9 @@ static inline unsigned grid_for(size_t n, unsigned block = 256) {
 // ============================================================================================ Ensemble
 
 void Ensemble::generate(Psi& psi, SampleSet& S) {
+    // collectives of this evaluation run iff the ensemble is sharded (an unsharded ensemble is never summed over ranks;
+    // a sharded one without a transport reports this shard's partial sums -- rank emulation in one process, tests)
+    set_reduce(world > 1);
     if(is_mc) {
         ANGPU_REQUIRE(num_chains >= 1 && num_samples >= 1, "MonteCarlo: num_samples and num_markov_chains must be positive");
         size_t c0, cn; shard(num_chains, c0, cn);
@@ -865,7 +860,7 @@ void Ensemble::generate(Psi& psi, SampleSet& S) {
         mc.num_chains_local = (unsigned)cn; mc.chain0 = (unsigned)c0;
         mc.seed_lo = (unsigned)seed; mc.seed_hi = (unsigned)(seed >> 32); mc.call = call;
         S.resize((size_t)mc.steps_per_chain * cn, psi.words);
-        d_acc_rej.resize(2); d_acc_rej.zero();
+        d_acc_rej.resize(4); d_acc_rej.zero();
         psi.mc_sample(mc, S, d_acc_rej.p);
         if(S.ns) { k_fill<<<grid_for(S.ns), 256, 0, stream()>>>(S.weight.p, 1.0 / (double)num_samples, S.ns); ANGPU_CHECK_LAUNCH(); count_launch(); }
         call++;
@@ -895,7 +890,7 @@ void Ensemble::generate_reweighted(Psi& psi, Psi& psi_sampling, SampleSet& S) {
 }
 void Ensemble::acceptance(unsigned long long out[2]) {
     out[0] = out[1] = 0;
-    if(d_acc_rej.n == 2) d_acc_rej.download(out, 2);
+    if(d_acc_rej.n >= 2) d_acc_rej.download(out, 2);
 }
 
 // ============================================================================================ ExpectationValue
@@ -1059,6 +1054,7 @@ void TDVP::eval(const Operator& op, Psi& psi, Ensemble& ens, bool want_S, Psi* p
     mark(0);
     if(psi_sampling) ens.generate_reweighted(psi, *psi_sampling, S);
     else ens.generate(psi, S);
+    sharded = ens.world > 1;
     mark(1);
     psi.eloc(op, S);
     mark(2);
@@ -1108,6 +1104,7 @@ void TDVP::ensure_dense_O(Psi* psi) {
 }
 
 void TDVP::build_S() {
+    set_reduce(sharded);
     ANGPU_REQUIRE(evaluated, "TDVP: call eval first");
     ensure_dense_O(last_psi);
     mark(5);
@@ -1205,7 +1202,7 @@ void TDVP::matvec(const cplx* v_dev, cplx* out_dev, const cplx* dot_dev, const d
         dot_dev = dot;
     }
     const ColPartials cp = col_reduce_partials(*this, row_a.p, false);
-    if(has_allreduce()) {
+    if(reduce_on()) {
         k_sum_chunks<<<grid_for(P), 256, 0, stream()>>>(cp.x, cp.chunks, P, out_dev);
         ANGPU_CHECK_LAUNCH(); count_launch();
         allreduce_sum(reinterpret_cast<double*>(out_dev), 2 * (size_t)P);
@@ -1217,6 +1214,7 @@ void TDVP::matvec(const cplx* v_dev, cplx* out_dev, const cplx* dot_dev, const d
 }
 void TDVP::S_dot_vector_dev(const cplx* v_dev, cplx* out_dev) { matvec(v_dev, out_dev, nullptr, nullptr, 0.0, 0.0); }
 void TDVP::S_dot_vector(const cplx* v_host, cplx* out_host) {
+    set_reduce(sharded);
     vec_in.upload(v_host, P);
     vec_out.resize(P);
     S_dot_vector_dev(vec_in.p, vec_out.p);
@@ -1244,6 +1242,7 @@ static void tdvp_diag(TDVP& t, DevBuf<double>& dbuf) {
 
 int TDVP::solve_cg(double tol, unsigned max_iter, double shift_abs, double shift_rel, cplx rhs_phase, cplx* x_host, double* rel_res_out) {
     ANGPU_REQUIRE(evaluated, "TDVP: call eval / eval_F first");
+    set_reduce(sharded);
     // with a dense S at hand (eval) the products stream S; ANGPU_CG_MATRIX_FREE=1 forces the O-based products
     const char* env_free = getenv("ANGPU_CG_MATRIX_FREE");
     const bool force_free = env_free && env_free[0] == '1';
@@ -1276,7 +1275,7 @@ int TDVP::solve_cg(double tol, unsigned max_iter, double shift_abs, double shift
     // sample-based products: the S.v epilogue, p.Ap, |r|^2 and Obar.p ride in three fused vector kernels (5 launches per
     // iteration; with several ranks the per-rank column sums are all-reduced before the epilogue); products on the dense S
     // use the generic matvec + a separate dot product
-    const bool fused = !use_S && (S.ns > 0 || has_allreduce());
+    const bool fused = !use_S && (S.ns > 0 || reduce_on());
     // convergence is decided on values summed over ranks, so that every rank takes the same decision
     auto read_rs = [&](int slot) -> double {      // |r|^2 = the imaginary slot of the (r.z, |r|^2) pair
         double* chk = d_scal.p + 12;
@@ -1297,7 +1296,7 @@ int TDVP::solve_cg(double tol, unsigned max_iter, double shift_abs, double shift
             if(fused) {
                 rowdot(p);
                 ColPartials cp = col_reduce_partials(*this, row_a.p, false);
-                if(has_allreduce()) {
+                if(reduce_on()) {
                     k_sum_chunks<<<grid_for(P), 256, 0, stream()>>>(cp.x, cp.chunks, P, Ap);
                     ANGPU_CHECK_LAUNCH(); count_launch();
                     allreduce_sum(reinterpret_cast<double*>(Ap), 2 * n);
@@ -1324,7 +1323,8 @@ int TDVP::solve_cg(double tol, unsigned max_iter, double shift_abs, double shift
         if(it > max_iter) it = max_iter;
     }
     mark(6);
-    ANGPU_CUDA(cudaMemcpyAsync(x_host, x, sizeof(cplx) * n, cudaMemcpyDeviceToHost, stream()));
+    last_x = x;
+    if(x_host) ANGPU_CUDA(cudaMemcpyAsync(x_host, x, sizeof(cplx) * n, cudaMemcpyDeviceToHost, stream()));
     ANGPU_CUDA(cudaStreamSynchronize(stream()));
     if(profile) ANGPU_CUDA(cudaEventElapsedTime(&phase_ms[5], ev[5], ev[6]));
     return (int)it;
@@ -1333,6 +1333,7 @@ int TDVP::solve_cg(double tol, unsigned max_iter, double shift_abs, double shift
 static cusolverDnHandle_t g_cusolver = nullptr;
 void TDVP::solve_dense(double shift_abs, double shift_rel, cplx rhs_phase, cplx* x_host) {
     ANGPU_REQUIRE(evaluated, "TDVP: call eval first");
+    set_reduce(sharded);
     if(!have_S) build_S();
     mark(5);
     const size_t n = P;
@@ -1365,7 +1366,8 @@ void TDVP::solve_dense(double shift_abs, double shift_rel, cplx rhs_phase, cplx*
     k_conj_inplace<<<grid_for(n), 256, 0, stream()>>>(b.p, n);
     ANGPU_CHECK_LAUNCH(); count_launch();
     mark(6);
-    b.download(x_host, n);
+    last_x = b.p;
+    if(x_host) b.download(x_host, n); else ANGPU_CUDA(cudaStreamSynchronize(stream()));
     if(profile) ANGPU_CUDA(cudaEventElapsedTime(&phase_ms[5], ev[5], ev[6]));
 }
 

@@ -8,15 +8,9 @@
 // TDVP.cu.template:107-121, 260-263).
 #pragma once
 #include "psi.hpp"
+#include "comm.hpp"
 
 namespace angpu {
-
-// Multi-GPU: sum `count` doubles in place across ranks, stream-ordered on angpu's stream.
-// Registered by the host layer (torch.distributed / NCCL); null => single process.
-typedef void (*allreduce_fn)(void* dev_ptr, unsigned long long count, void* user);
-void set_allreduce(allreduce_fn fn, void* user);
-void allreduce_sum(double* dev_ptr, size_t count);
-bool has_allreduce();
 
 struct Ensemble {
     bool is_mc = false;
@@ -27,7 +21,8 @@ struct Ensemble {
     unsigned num_sweeps = 0, num_therm = 0, num_chains = 0, call = 0;
     uint64_t seed = 0xA11CE;
     // sharding: this process owns chains / basis indices [begin, begin+count) of the global range
-    unsigned rank = 0, world = 1;
+    // (a new ensemble inherits the communicator's rank / world: angpu_comm_init, comm.hpp)
+    unsigned rank = (unsigned)comm_rank(), world = (unsigned)comm_world();
     DevBuf<unsigned long long> d_acc_rej;
 
     size_t num_steps() const { return is_mc ? (size_t)num_samples : ((size_t)1 << num_sites); }
@@ -77,6 +72,8 @@ struct TDVP {
     DevBuf<cplx> chunk_buf, row_a, vec_in, vec_out, cg_buf, vb_part, ones;
     DevBuf<double> d_scal;
     bool have_dense_O = false, factorised = false, have_S = false, evaluated = false;
+    const cplx* last_x = nullptr;            // device solution of the last solve_cg / solve_dense (valid until the next solve)
+    bool sharded = false;                    // the samples of the last eval are one rank's share: later products / solves sum over ranks
     unsigned rbm_N = 0, rbm_M = 0, words = 1;
     cplx E{0.0, 0.0}; double E2 = 0.0, total_weight = 0.0;
     unsigned long long num_steps_global = 0;

@@ -4,8 +4,11 @@ The hot path shards with no data-path exchange: Markov chains (and ExactSummatio
 rank r of G owns the chains / indices [r*n/G, (r+1)*n/G) — Philox streams are keyed by the GLOBAL chain id, so the
 sampled configurations do not depend on G.  The only communication is the sum of the packed partial sums
 {sum w E, sum w |E|^2, sum w, sum w O_k, sum w E O_k*} (one all-reduce per functional), the S-matrix partial
-(dense SR) or one P-vector per CG iteration (matrix-free SR).  libangpu calls back into `allreduce_hook` at those
-points; the hook wraps the device pointer in a torch tensor (no copy) and runs `dist.all_reduce` on it.
+(dense SR) or one P-vector per CG iteration (matrix-free SR).  libangpu owns an NCCL communicator for these sums
+(`angpu_comm_init`, csrc/comm.cu): `init_from_env` creates the unique id on rank 0, broadcasts its 128 bytes through
+`torch.distributed` and initialises the library's communicator on every rank, so the collectives are plain
+`ncclAllReduce` calls on the library's stream -- no Python in the loop.  `ANGPU_COMM=hook` selects the older transport,
+a callback into `allreduce_hook` (dist.all_reduce on a zero-copy view of the device pointer).
 
 The reference has no counterpart (single device, no collectives — SURVEY.md §2).
 """
@@ -68,7 +71,17 @@ def init_from_env(backend="nccl"):
             dist.init_process_group(backend=backend, rank=rank, world_size=world,
                                     device_id=torch.device("cuda", local_rank),
                                     timeout=datetime.timedelta(seconds=int(os.environ.get("ANGPU_NCCL_TIMEOUT_S", "120"))))
-        api.set_allreduce(allreduce_hook)
+        if os.environ.get("ANGPU_COMM", "nccl") == "hook":
+            api.set_allreduce(allreduce_hook)
+            # ensembles do not inherit a shard from the callback transport: callers use .set_shard(rank, world)
+        else:
+            uid = torch.zeros(128, dtype=torch.uint8)
+            if rank == 0:
+                uid = torch.frombuffer(bytearray(api.comm_unique_id()), dtype=torch.uint8).clone()
+            dev = torch.device("cuda", local_rank) if backend == "nccl" else torch.device("cpu")
+            uid = uid.to(dev)
+            dist.broadcast(uid, src=0)
+            api.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
     return rank, world
 
 
@@ -76,6 +89,7 @@ def shutdown():
     _views.clear()
     api.set_allreduce(None)
     api.synchronize()
+    api.comm_destroy()
     api.set_stream(None)
     if dist.is_initialized():
         dist.destroy_process_group()

@@ -50,9 +50,22 @@ int angpu_profiler_start(void);
 int angpu_profiler_stop(void);
 /* number of kernels launched by the library since the last call with reset != 0 */
 unsigned long long angpu_launch_count(int reset);
-/* Multi-GPU hook (no reference counterpart; the reference is single-device): sums `count` doubles at `dev_ptr`
- * in place over all ranks, ordered on the library's stream.  Every reduction of every functional goes through it. */
-typedef void (*angpu_allreduce_fn)(void* dev_ptr, unsigned long long count, void* user);
+/* Multi-GPU (no reference counterpart; the reference is single-device).  One process per GPU.  The library owns an NCCL
+ * communicator (libnccl.so.2 is opened at run time; single-GPU users never load it) and sums the partial results of
+ * SHARDED ensembles (angpu_ensemble_set_shard / inherited rank, world) over ranks on its own stream:
+ *   rank 0:      angpu_comm_unique_id(id)   -> ship the 128 bytes to every rank by any means (file, MPI, torch.distributed)
+ *   every rank:  angpu_init(device); angpu_comm_init(id, rank, world)
+ * Ensembles created afterwards own the chains / basis indices of `rank` out of `world`.  angpu_comm_init(.., 0, 1) or
+ * angpu_comm_destroy() return to single-process operation. */
+#define ANGPU_COMM_ID_BYTES 128
+int angpu_comm_unique_id(unsigned char id_out[ANGPU_COMM_ID_BYTES]);
+int angpu_comm_init(const unsigned char id[ANGPU_COMM_ID_BYTES], int rank, int world);
+int angpu_comm_destroy(void);
+int angpu_comm_rank(int* rank_out, int* world_out);
+/* Alternative transport for hosts that own their communicator: a callback that sums `count` doubles at `dev_ptr` in
+ * place over all ranks, ordered on the library's stream, and returns 0 on success (non-zero makes the calling entry
+ * point fail instead of continuing with un-reduced partial sums).  Used only while no NCCL communicator is installed. */
+typedef int (*angpu_allreduce_fn)(void* dev_ptr, unsigned long long count, void* user);
 int angpu_set_allreduce(angpu_allreduce_fn fn, void* user);
 
 /* ---- basis / operator primitives ----------------------------------------------------------------------- */
@@ -118,6 +131,14 @@ int angpu_ensemble_local_steps(angpu_ensemble_t ens, unsigned long long* out);  
 int angpu_ensemble_set_shard(angpu_ensemble_t ens, unsigned rank, unsigned world);
 /* acceptances_ar / rejections_ar of the last call (include/ensembles/MonteCarlo.hpp:164-169), this process' chains */
 int angpu_mc_acceptance(angpu_ensemble_t ens, unsigned long long out[2]);
+/* Position of the Monte-Carlo random streams: the number of sampling calls made so far (the Philox counter block; the
+ * reference's persistent per-chain RNG state).  Setting it replays / aligns streams between ensembles. */
+int angpu_mc_get_call_index(angpu_ensemble_t ens, unsigned* out);
+int angpu_mc_set_call_index(angpu_ensemble_t ens, unsigned call_index);
+/* sampler counters of the last call: out[0..1] as angpu_mc_acceptance, out[2] = proposals whose accept/reject decision
+ * needed the fp64 evaluation (the fp32-screened PsiRBM sampler, csrc/rbm_sampler.cuh; 0 for the all-fp64 samplers),
+ * out[3] reserved (0).  No reference counterpart. */
+int angpu_mc_counters(angpu_ensemble_t ens, unsigned long long out[4]);
 /* Runs the sampler once and copies this process' configurations [local_steps][words] and log psi out (testing aid). */
 int angpu_ensemble_sample(angpu_ensemble_t ens, angpu_psi_t psi, uint64_t* confs_out, double* log_psi_out);
 
@@ -176,6 +197,9 @@ int angpu_tdvp_S_dot_vector(angpu_tdvp_t tdvp, const double* vec, double* out); 
 int angpu_tdvp_solve_cg(angpu_tdvp_t tdvp, double tol, unsigned max_iter, double shift_abs, double shift_rel,
                         const double rhs_phase[2], double* x_out, unsigned* iterations_out, double* rel_residual_out);
 int angpu_tdvp_solve_dense(angpu_tdvp_t tdvp, double shift_abs, double shift_rel, const double rhs_phase[2], double* x_out);
+/* x_out may be NULL in both solvers: the solution then stays on the device, and
+ * angpu_tdvp_apply_update performs the SR / TDVP step  params(psi) += alpha * x  there (no host round trip of P numbers). */
+int angpu_tdvp_apply_update(angpu_tdvp_t tdvp, angpu_psi_t psi, const double alpha[2]);
 /* NEW, opt-in: rebuild S from the samples of the last eval on the tcgen05 tensor cores (3xTF32 split, fp32 accumulation in
  * TMEM; ~1e-5 relative to ||S||).  angpu_tdvp_eval itself builds S in exact fp64 (the reference: fp64 atomics, :216-279). */
 int angpu_tdvp_build_S_tensorcore(angpu_tdvp_t tdvp);
