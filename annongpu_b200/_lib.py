@@ -88,6 +88,7 @@ _SIGNATURES = {
     "angpu_tdvp_destroy": [vp],
     "angpu_tdvp_eval": [vp, vp, vp, vp],
     "angpu_tdvp_eval_F": [vp, vp, vp, vp],
+    "angpu_tdvp_eval_tol": [vp, vp, vp, vp, dbl],
     "angpu_kl_create": [u32, vp],
     "angpu_kl_destroy": [vp],
     "angpu_kl_set_log_psi_scale": [vp, dbl],

@@ -490,6 +490,15 @@ class PsiFullyPolarized:
             lib.angpu_psi_destroy(self._handle)
             self._handle = None
 
+    def to_json(self):
+        """pyANNonGPU/PsiFullyPolarized.py:4-10."""
+        return dict(type="PsiFullyPolarized", num_sites=self.num_sites, log_prefactor_re=self.log_prefactor.real,
+                    log_prefactor_im=self.log_prefactor.imag)
+
+    @staticmethod
+    def from_json(obj):
+        return PsiFullyPolarized(obj["num_sites"], obj["log_prefactor_re"] + 1j * obj["log_prefactor_im"])
+
 
 class _PsiClassical(_Psi):
     _order = 1
@@ -515,6 +524,35 @@ class _PsiClassical(_Psi):
 
     def update_psi_ref_kernel(self):
         pass
+
+    def to_json(self, ansatz=None):
+        """pyANNonGPU/PsiClassical.py:7-25 (same keys).  `ansatz`: the local operators as PauliSum expressions; defaults
+        to the expressions the H_local operators were built from."""
+        from .json_numpy import plain
+        if ansatz is None:
+            ansatz = [PauliSum(op.num_sites, list(op.coefficients), list(op.a_masks), list(op.b_masks)) for op in self.H_local]
+        ref = self.psi_ref.to_json() if hasattr(self.psi_ref, "to_json") else self.psi_ref
+        return plain(dict(type="PsiClassical", num_sites=self.num_sites, order=self.order, ansatz=[a.to_json() for a in ansatz],
+                          params=self.params[:len(self.H_local)],
+                          psi_ref=ref, log_prefactor_re=self.log_prefactor.real, log_prefactor_im=self.log_prefactor.imag))
+
+    @staticmethod
+    def from_json(json_obj, gpu=True):
+        """pyANNonGPU/PsiClassical.py:28-67: PsiClassical{FP,ANN}_{1,2} by `order` and the type of psi_ref."""
+        from .json_numpy import restore
+        obj = restore(json_obj)
+        kind = obj["psi_ref"]["type"]
+        if kind == "PsiFullyPolarized":
+            psi_ref = PsiFullyPolarized.from_json(obj["psi_ref"])
+        elif kind == "PsiCNN":
+            psi_ref = PsiCNN.from_json(obj["psi_ref"], gpu)
+        else:
+            raise ValueError(f"PsiClassical.from_json: reference state of type {kind} is not supported (PsiFullyPolarized, PsiCNN)")
+        H_local = [Operator(PauliSum.from_json(h), gpu, num_sites=obj["num_sites"]) for h in obj["ansatz"]]
+        lp = obj["log_prefactor_re"] + 1j * obj["log_prefactor_im"]
+        cls = {(1, True): PsiClassicalFP_1, (2, True): PsiClassicalFP_2, (1, False): PsiClassicalANN_1,
+               (2, False): PsiClassicalANN_2}[(int(obj["order"]), kind == "PsiFullyPolarized")]
+        return cls(obj["num_sites"], H_local, np.asarray(obj["params"]), psi_ref, lp, gpu)
 
 
 class PsiClassicalFP_1(_PsiClassical):
@@ -789,10 +827,15 @@ class TDVP:
             lib.angpu_tdvp_destroy(self._h)
             self._h = None
 
-    def eval(self, operator, psi, ensemble):
+    def eval(self, operator, psi, ensemble, s_tolerance=0.0):
+        """TDVP::eval.  `s_tolerance` (additive): 0 = S in exact fp64; >= 1e-5 (relative to ||S||) = S on the tcgen05
+        tensor cores (3xTF32, ~2e-6 measured), several times faster for P ~ 1e4."""
         op = _match(operator, psi)
         self._keep = (op, psi, ensemble)
-        call("angpu_tdvp_eval", self._h, op._h, psi._h, ensemble._h)
+        if s_tolerance:
+            call("angpu_tdvp_eval_tol", self._h, op._h, psi._h, ensemble._h, float(s_tolerance))
+        else:
+            call("angpu_tdvp_eval", self._h, op._h, psi._h, ensemble._h)
 
     def eval_F(self, operator, psi, ensemble):
         op = _match(operator, psi)

@@ -335,6 +335,13 @@ int angpu_tdvp_eval_reweighted(angpu_tdvp_t tdvp, angpu_operator_t op, angpu_psi
 int angpu_tdvp_eval(angpu_tdvp_t tdvp, angpu_operator_t op, angpu_psi_t psi, angpu_ensemble_t ens) {
     API_BEGIN NOTNULL(tdvp); NOTNULL(op); NOTNULL(psi); NOTNULL(ens); tdvp->t->eval(*op->p, *psi->p, ens->e, true); API_END
 }
+int angpu_tdvp_eval_tol(angpu_tdvp_t tdvp, angpu_operator_t op, angpu_psi_t psi, angpu_ensemble_t ens, double s_tolerance) {
+    API_BEGIN NOTNULL(tdvp); NOTNULL(op); NOTNULL(psi); NOTNULL(ens);
+    ANGPU_REQUIRE(s_tolerance == 0.0 || s_tolerance >= 1e-5, "s_tolerance: 0 (exact fp64 S) or >= 1e-5 (tensor-core S)");
+    if(s_tolerance == 0.0) tdvp->t->eval(*op->p, *psi->p, ens->e, true);
+    else { tdvp->t->eval(*op->p, *psi->p, ens->e, false); tdvp->t->build_S_tensorcore(); }
+    API_END
+}
 int angpu_tdvp_eval_F(angpu_tdvp_t tdvp, angpu_operator_t op, angpu_psi_t psi, angpu_ensemble_t ens) {
     API_BEGIN NOTNULL(tdvp); NOTNULL(op); NOTNULL(psi); NOTNULL(ens); tdvp->t->eval_F(*op->p, *psi->p, ens->e); API_END
 }

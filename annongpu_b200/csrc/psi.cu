@@ -232,11 +232,10 @@ void PsiRBM::compute_T(SampleSet& S, DevBuf<cplx>& T) {
 }
 void PsiRBM::ok_rows(SampleSet& S, size_t s0, size_t cnt, cplx* out) {
     if(cnt == 0) return;
-    DevBuf<cplx> T;
+    DevBuf<cplx>& T = T_scratch;                   // grow-only member: no allocation / stream sync per call
     compute_T(S, T);
     k_rbm_dense_O<<<(unsigned)cnt, 256, 0, stream()>>>(dev(), S.conf.p + s0 * words, T.p + s0 * M, cnt, out);
     ANGPU_CHECK_LAUNCH(); count_launch();
-    ANGPU_CUDA(cudaStreamSynchronize(stream()));   // T is freed on return
 }
 
 template<int K, int WORDS>

@@ -60,6 +60,7 @@ struct PsiRBM : Psi {
     cplx fw{1.0, 0.0};
     mutable std::vector<cplx> hW;
     DevBuf<cplx> dW, dWpad;
+    DevBuf<cplx> T_scratch;             // factorised rows for ok_rows (dense O on request)
     DevBuf<float4> dWf;                 // fp32 copy of W in the screened sampler's layout (rbm_sampler.cuh), M <= 512
     unsigned Mpad = 0;
     const cplx* Wpad() const { return Mpad == M ? dW.p : dWpad.p; }

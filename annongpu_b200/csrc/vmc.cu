@@ -1228,7 +1228,8 @@ static void tdvp_diag(TDVP& t, DevBuf<double>& dbuf) {
     unsigned chunks = (unsigned)std::max<size_t>(1, std::min<size_t>(256, ns / 64));
     const size_t chunk = ns ? (ns + chunks - 1) / chunks : 1;
     chunks = ns ? (unsigned)((ns + chunk - 1) / chunk) : 1;
-    DevBuf<double> part((size_t)chunks * period);
+    DevBuf<double>& part = t.diag_part;               // grow-only member: no cudaMalloc / cudaFree / stream sync per call
+    part.resize((size_t)chunks * period);
     if(ns == 0) part.zero();
     else if(t.factorised) k_diag_rbm<<<dim3(ceil_div(period, 128), chunks), 128, 0, stream()>>>(t.T.p, t.S.weight.p, ns, t.rbm_M, chunk, part.p);
     else k_diag_dense<<<dim3(ceil_div(period, 128), chunks), 128, 0, stream()>>>(t.O.p, t.S.weight.p, ns, t.P, chunk, part.p);
@@ -1237,7 +1238,6 @@ static void tdvp_diag(TDVP& t, DevBuf<double>& dbuf) {
     allreduce_sum(dbuf.p, t.P);
     k_diag_finalize<<<grid_for(t.P), 256, 0, stream()>>>(dbuf.p, t.Ok_dev(), t.P);
     ANGPU_CHECK_LAUNCH(); count_launch();
-    ANGPU_CUDA(cudaStreamSynchronize(stream()));      // `part` is freed on return
 }
 
 int TDVP::solve_cg(double tol, unsigned max_iter, double shift_abs, double shift_rel, cplx rhs_phase, cplx* x_host, double* rel_res_out) {

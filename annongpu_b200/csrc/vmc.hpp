@@ -70,7 +70,7 @@ struct TDVP {
     DevBuf<cplx> O;                          // dense O_k_samples [ns][P] (valid iff have_dense_O)
     DevBuf<cplx> T;                          // PsiRBM factorised form [ns][M] (valid iff factorised)
     DevBuf<cplx> chunk_buf, row_a, vec_in, vec_out, cg_buf, vb_part, ones;
-    DevBuf<double> d_scal;
+    DevBuf<double> d_scal, diag_part;
     bool have_dense_O = false, factorised = false, have_S = false, evaluated = false;
     const cplx* last_x = nullptr;            // device solution of the last solve_cg / solve_dense (valid until the next solve)
     bool sharded = false;                    // the samples of the last eval are one rank's share: later products / solves sum over ranks

@@ -103,8 +103,8 @@ class PauliSum:
     def __add__(self, other):
         if isinstance(other, (int, float, complex)):
             other = PauliSum(self.num_sites).add(other, {})
-        assert other.num_sites == self.num_sites
-        return PauliSum(self.num_sites, self.coeffs + other.coeffs, self.a + other.a, self.b + other.b).simplified()
+        # (expressions built site by site, e.g. sigma_z(0) * sigma_z(1), grow to the larger support)
+        return PauliSum(max(self.num_sites, other.num_sites), self.coeffs + other.coeffs, self.a + other.a, self.b + other.b).simplified()
 
     __radd__ = __add__
 
@@ -136,8 +136,7 @@ class PauliSum:
     def __mul__(self, other):
         if isinstance(other, (int, float, complex)):
             return PauliSum(self.num_sites, [c * other for c in self.coeffs], list(self.a), list(self.b))
-        assert other.num_sites == self.num_sites
-        out = PauliSum(self.num_sites)
+        out = PauliSum(max(self.num_sites, other.num_sites))
         for c1, a1, b1 in zip(self.coeffs, self.a, self.b):
             for c2, a2, b2 in zip(other.coeffs, other.a, other.b):
                 ph, a, b = self._string_product(a1, b1, a2, b2)
@@ -161,6 +160,43 @@ class PauliSum:
     def commutator(self, other):
         return self * other - other * self
 
+    def exp(self, threshold=0.0):
+        """exp(self) as a PauliSum for a SINGLE Pauli string c P (P^2 = 1): cosh(c) 1 + sinh(c) P -- the only use the
+        reference makes of QuantumExpression's .exp (pyANNonGPU/LearningByGradientDescent.py:356, `term.exp(0)`, the
+        factors of a Trotterised propagator).  Terms with |coefficient| <= threshold are dropped."""
+        t = self.simplified()
+        if t.num_strings == 0:
+            return PauliSum(self.num_sites).add(1.0, {})
+        if t.num_strings != 1:
+            raise ValueError("PauliSum.exp is defined for a single Pauli string (factor a sum term by term)")
+        c, a, b = t.coeffs[0], t.a[0], t.b[0]
+        if a == 0 and b == 0:
+            return PauliSum(self.num_sites).add(np.exp(c), {})
+        import cmath
+        out = PauliSum(self.num_sites, [cmath.cosh(c), cmath.sinh(c)], [0, a], [0, b])
+        return out.simplified(threshold)
+
+    def to_json(self):
+        """{"type": "PauliSum", "num_sites": N, "terms": [{"re": .., "im": .., "paulis": {"3": "X", ...}}, ...]}
+        (QuantumExpression's own PauliExpression.to_json encoding is not available -- the dependency is absent and
+        unpinned, SURVEY.md 8c -- so operators inside JSON documents use this self-describing form)."""
+        terms = []
+        for c, a, b in zip(self.coeffs, self.a, self.b):
+            paulis = {}
+            for i in range(self.num_sites):
+                code = ((a >> i) & 1) | (((b >> i) & 1) << 1)
+                if code:
+                    paulis[str(i)] = " XYZ"[code]
+            terms.append({"re": c.real, "im": c.imag, "paulis": paulis})
+        return {"type": "PauliSum", "num_sites": self.num_sites, "terms": terms}
+
+    @staticmethod
+    def from_json(obj):
+        out = PauliSum(int(obj["num_sites"]))
+        for t in obj["terms"]:
+            out.add(complex(t["re"], t["im"]), {int(k): v for k, v in t["paulis"].items()})
+        return out
+
     def matrix(self):
         """Dense 2^N x 2^N matrix with the reference's conventions: basis index = configuration bitmask (bit i <-> site i,
         1 <-> spin up), M[s, s'] = sum_n c_n <s| P_n |s'> as used by E_loc(s) = sum_s' M[s, s'] psi(s') / psi(s)
@@ -175,6 +211,19 @@ class PauliSum:
             coeff = c * ((-1j) ** ny) * np.where(neg, -1.0, 1.0)
             M[s, s ^ (a ^ b)] += coeff
         return M
+
+
+def sigma_x(site, num_sites=None):
+    """QuantumExpression-style constructors: sigma_x(i), sigma_y(i), sigma_z(i) (the support grows under + and *)."""
+    return PauliSum(num_sites or site + 1).add(1.0, {site: "X"})
+
+
+def sigma_y(site, num_sites=None):
+    return PauliSum(num_sites or site + 1).add(1.0, {site: "Y"})
+
+
+def sigma_z(site, num_sites=None):
+    return PauliSum(num_sites or site + 1).add(1.0, {site: "Z"})
 
 
 def propagator(H, dt):

@@ -178,6 +178,10 @@ int angpu_tdvp_create(unsigned num_params, angpu_tdvp_t* out);
 int angpu_tdvp_destroy(angpu_tdvp_t tdvp);
 int angpu_tdvp_eval(angpu_tdvp_t tdvp, angpu_operator_t op, angpu_psi_t psi, angpu_ensemble_t ens);    /* eval, :182-302 */
 int angpu_tdvp_eval_F(angpu_tdvp_t tdvp, angpu_operator_t op, angpu_psi_t psi, angpu_ensemble_t ens);  /* eval_F_vector, :306-334 */
+/* eval with an accuracy budget for S: s_tolerance = 0 builds S in exact fp64 (= angpu_tdvp_eval); s_tolerance >= 1e-5 (relative
+ * to ||S||) selects the tcgen05 tensor-core build (3xTF32 split, fp32 accumulation in TMEM; measured ~2e-6), 8x faster at C4.
+ * E, F, <O_k> and O_k_samples are fp64 either way.  Values in (0, 1e-5) are an error.  Additive, no reference counterpart. */
+int angpu_tdvp_eval_tol(angpu_tdvp_t tdvp, angpu_operator_t op, angpu_psi_t psi, angpu_ensemble_t ens, double s_tolerance);
 /* eval_with_psi_ref = TDVP::eval(..., true_t) (TDVP.hpp:90-93, TDVP.cu.template:15-74): samples from psi_sampling (the
  * reference passes psi.psi_ref of a PsiClassical), weights w_s |psi(s)/psi_sampling(s)|^2, sums NOT normalised;
  * total_weight (angpu_tdvp_get_scalars) = sum of those weights for THIS call (the reference never clears it).

@@ -20,6 +20,53 @@ def build(tmp_path):
     return exe
 
 
+def build_two_ranks(tmp_path):
+    exe = str(tmp_path / "vmc_two_ranks")
+    libdir = os.path.join(ROOT, "annongpu_b200")
+    cmd = ["gcc", "-std=gnu99", "-Wall", "-O1", os.path.join(ROOT, "tests", "cabi", "vmc_two_ranks.c"), "-I", os.path.join(ROOT, "include"),
+           "-L", libdir, "-langpu", "-lm", "-Wl,-rpath," + libdir, "-o", exe]
+    subprocess.run(cmd, check=True)
+    return exe
+
+
+def test_two_rank_c_program_compiles_and_links(tmp_path):
+    assert os.path.exists(build_two_ranks(tmp_path))
+
+
+@pytest.mark.gpu
+def test_two_ranks_from_plain_c(tmp_path):
+    """libangpu's own NCCL communicator driven from C: two forked ranks reproduce the one-rank E and F to 1e-10."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = subprocess.run([build_two_ranks(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.startswith("E2 ")
+
+
+def build_cxx(tmp_path):
+    exe = str(tmp_path / "vmc_from_cxx")
+    libdir = os.path.join(ROOT, "annongpu_b200")
+    cmd = ["g++", "-std=c++14", "-Wall", "-O1", os.path.join(ROOT, "tests", "cabi", "vmc_from_cxx.cpp"), "-I", os.path.join(ROOT, "include"),
+           "-L", libdir, "-langpu", "-Wl,-rpath," + libdir, "-o", exe]
+    subprocess.run(cmd, check=True)
+    return exe
+
+
+def test_cxx_program_compiles_and_links(tmp_path):
+    """CPU: include/angpu.hpp (the RAII classes with the reference's names) is valid C++14 over the C ABI."""
+    assert os.path.exists(build_cxx(tmp_path))
+
+
+@pytest.mark.gpu
+def test_cxx_program_runs_and_matches_the_c_program(tmp_path, gpu):
+    rc = subprocess.run([build(tmp_path)], capture_output=True, text=True, timeout=300)
+    rx = subprocess.run([build_cxx(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert rc.returncode == 0 and rx.returncode == 0, rc.stderr + rx.stderr
+    tc, tx = rc.stdout.split(), rx.stdout.split()
+    assert abs(float(tc[1]) - float(tx[1])) <= 1e-12 and int(tc[6]) == int(tx[4])      # same E, same CG iteration count
+
+
 def test_c_program_compiles_and_links(tmp_path):
     """CPU: the header is valid C99 and every symbol the program uses resolves against the shared library."""
     assert os.path.exists(build(tmp_path))

@@ -345,6 +345,13 @@ def test_tensorcore_S_build_matches_fp64(gpu, name, ns_mc):
     scale = np.abs(S64).max()
     assert np.abs(S32 - S64).max() <= 1e-5 * scale
     assert np.abs(S32 - S32.conj().T).max() <= 1e-12 * scale
+    # the same path selected from eval by its accuracy budget (same samples: a fresh ensemble with the same seed)
+    ens2 = gpu.MonteCarloSpins(ns_mc, 1, 5, ns_mc, True, seed=11) if ns_mc else ens
+    t2 = gpu.TDVP(psi.num_params, True)
+    t2.eval(op, psi, ens2, s_tolerance=1e-5)
+    assert np.array_equal(t2.S_matrix, S32) and np.abs(t2.F_vector - t.F_vector).max() <= 1e-14 * np.abs(t.F_vector).max()
+    with pytest.raises(gpu.AngpuError):
+        t2.eval(op, psi, ens2, s_tolerance=1e-8)
     # un-normalised ExactSummation weights (sum w != 1): the reference's convention S = sum w O*O - <O>*<O> is kept
     if not ns_mc:
         psi.log_prefactor = psi.log_prefactor + 0.3
