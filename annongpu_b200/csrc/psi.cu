@@ -166,20 +166,36 @@ void PsiRBM::upload() {
         }
     }
 }
+// theta = sigma W for a batch of configurations: the FP64 tensor-core GEMM (k_rbm_angles_dmma) for batches that fill the
+// m8 tiles, the warp-per-configuration kernel for probes of a few configurations; ANGPU_ANGLES=fma forces the latter
+static void rbm_angles(const RbmDev& d, const uint64_t* confs, size_t ns, cplx* angles, cplx* log_psi, double* weight) {
+    static const bool force_fma = [] { const char* e = getenv("ANGPU_ANGLES"); return e && std::string(e) == "fma"; }();
+    if(ns >= 64 && !force_fma) {
+        const bool wide = 2u * d.M > 64u;
+        static bool attr = false;
+        if(!attr) {
+            ANGPU_CUDA(cudaFuncSetAttribute(k_rbm_angles_dmma<8, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ag_smem(128)));
+            ANGPU_CUDA(cudaFuncSetAttribute(k_rbm_angles_dmma<8, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ag_smem(64)));
+            attr = true;
+        }
+        if(wide) k_rbm_angles_dmma<8, 128><<<ceil_div(ns, 64), 256, ag_smem(128), stream()>>>(d, confs, ns, angles, log_psi, weight);
+        else k_rbm_angles_dmma<8, 64><<<ceil_div(ns, 64), 256, ag_smem(64), stream()>>>(d, confs, ns, angles, log_psi, weight);
+    } else {
+        const unsigned wpb = 8, grid = (unsigned)std::min<size_t>((ns + wpb - 1) / wpb, (size_t)ctx().num_sms * 16);
+        k_rbm_angles<<<grid, wpb * 32, 0, stream()>>>(d, confs, ns, angles, log_psi, weight);
+    }
+    ANGPU_CHECK_LAUNCH(); count_launch();
+}
 void PsiRBM::log_psi(SampleSet& S, bool es_weights) {
     if(S.ns == 0) return;
     S.angles.resize(S.ns * M);
-    const unsigned wpb = 8, grid = (unsigned)std::min<size_t>((S.ns + wpb - 1) / wpb, (size_t)ctx().num_sms * 16);
-    k_rbm_angles<<<grid, wpb * 32, 0, stream()>>>(dev(), S.conf.p, S.ns, S.angles.p, S.log_psi.p, es_weights ? S.weight.p : nullptr);
-    ANGPU_CHECK_LAUNCH(); count_launch();
+    rbm_angles(dev(), S.conf.p, S.ns, S.angles.p, S.log_psi.p, es_weights ? S.weight.p : nullptr);
     S.has_angles = true;
 }
 void PsiRBM::ensure_angles(SampleSet& S) {
     if(S.has_angles || S.ns == 0) return;
     S.angles.resize(S.ns * M);
-    const unsigned wpb = 8, grid = (unsigned)std::min<size_t>((S.ns + wpb - 1) / wpb, (size_t)ctx().num_sms * 16);
-    k_rbm_angles<<<grid, wpb * 32, 0, stream()>>>(dev(), S.conf.p, S.ns, S.angles.p, nullptr, nullptr);
-    ANGPU_CHECK_LAUNCH(); count_launch();
+    rbm_angles(dev(), S.conf.p, S.ns, S.angles.p, nullptr, nullptr);
     S.has_angles = true;
 }
 template<int WPS>
@@ -238,14 +254,25 @@ void PsiRBM::ok_rows(SampleSet& S, size_t s0, size_t cnt, cplx* out) {
     ANGPU_CHECK_LAUNCH(); count_launch();
 }
 
+// initial configurations + theta_0 = sigma_0 W (tensor-core GEMM) into the chains' first sample slots; false when there is
+// no slot to use (no recorded sample), in which case the samplers initialise themselves
+static bool rbm_preinit(const RbmDev& d, const McParams& mc, SampleSet& S) {
+    if(mc.steps_per_chain == 0u) return false;
+    k_mc_init_conf<<<ceil_div(mc.num_chains_local, 128), 128, 0, stream()>>>(mc, d.N, d.words, S.conf.p);
+    ANGPU_CHECK_LAUNCH(); count_launch();
+    rbm_angles(d, S.conf.p, mc.num_chains_local, S.angles.p, nullptr, nullptr);
+    return true;
+}
+
 template<int K, int WORDS>
 static void launch_mc_rbm(const RbmDev& d, const cplx* Wp, const McParams& mc, SampleSet& S, unsigned long long* acc_rej_dev) {
     const unsigned wpb = MC_RBM_THREADS / 32, grid = ceil_div(mc.num_chains_local, wpb);
     // the fp64 sampler (complex final weight, or ANGPU_MC_SCREEN=0): resident blocks per SM requested from ptxas: 8
     // (<= 128 registers); for K = 8 with one-word configurations 10 blocks = 20 warps per SM fit in 96 registers
     constexpr int MINB = (K == 8 && WORDS == 1) ? 10 : (K <= 8) ? 8 : 1;
-    if(d.fw.im == 0.0) k_mc_rbm<K, WORDS, true, MINB><<<grid, wpb * 32, 0, stream()>>>(d, Wp, mc, S.conf.p, S.log_psi.p, S.angles.p, acc_rej_dev);
-    else k_mc_rbm<K, WORDS, false, MINB><<<grid, wpb * 32, 0, stream()>>>(d, Wp, mc, S.conf.p, S.log_psi.p, S.angles.p, acc_rej_dev);
+    cplx* angles = rbm_preinit(d, mc, S) ? S.angles.p : nullptr;      // non-null: the chains start from the pre-computed theta_0
+    if(d.fw.im == 0.0) k_mc_rbm<K, WORDS, true, MINB><<<grid, wpb * 32, 0, stream()>>>(d, Wp, mc, S.conf.p, S.log_psi.p, angles, acc_rej_dev);
+    else k_mc_rbm<K, WORDS, false, MINB><<<grid, wpb * 32, 0, stream()>>>(d, Wp, mc, S.conf.p, S.log_psi.p, angles, acc_rej_dev);
     ANGPU_CHECK_LAUNCH(); count_launch();
 }
 // the fp32-screened sampler (rbm_sampler.cuh): real final weight
@@ -299,9 +326,10 @@ void PsiRBM::mc_sample(const McParams& mc, SampleSet& S, unsigned long long* acc
     } else if(M <= 2048u) {
         S.angles.resize(S.ns * M);
         const unsigned K = (M + MC_BLOCK_T - 1) / MC_BLOCK_T;          // 3..8
+        cplx* angles = rbm_preinit(d, mc, S) ? S.angles.p : nullptr;  // non-null: the chains start from the pre-computed theta_0
         auto launch = [&](auto kr, auto kc) {
-            if(d.fw.im == 0.0) kr<<<mc.num_chains_local, MC_BLOCK_T, 0, stream()>>>(d, Wpad(), mc, S.conf.p, S.log_psi.p, S.angles.p, acc_rej_dev);
-            else kc<<<mc.num_chains_local, MC_BLOCK_T, 0, stream()>>>(d, Wpad(), mc, S.conf.p, S.log_psi.p, S.angles.p, acc_rej_dev);
+            if(d.fw.im == 0.0) kr<<<mc.num_chains_local, MC_BLOCK_T, 0, stream()>>>(d, Wpad(), mc, S.conf.p, S.log_psi.p, angles, acc_rej_dev);
+            else kc<<<mc.num_chains_local, MC_BLOCK_T, 0, stream()>>>(d, Wpad(), mc, S.conf.p, S.log_psi.p, angles, acc_rej_dev);
         };
         switch(K) {
             case 3: launch(k_mc_rbm_block<3, true>, k_mc_rbm_block<3, false>); break;

@@ -16,6 +16,7 @@
 //  k_rbm_dense_O  materialises the dense rows only when a caller asks for O_k_samples / a dense S.
 #pragma once
 #include "kernels.cuh"
+#include "dmma.cuh"
 
 namespace angpu {
 
@@ -131,6 +132,22 @@ __device__ __forceinline__ void conf_flip_t(uint64_t (&c)[MAXW], unsigned site) 
     else conf_flip(c, site);
 }
 
+// Initial configurations of the chains (Init_Policy: a random bitmask, policies/Init_Policy.hpp:16-25) into the slots of
+// their first recorded sample; the batched angle GEMM (k_rbm_angles_dmma) then leaves theta_0 = sigma_0 W in the matching
+// angle slots, and the samplers start from there instead of accumulating N rows per chain themselves.
+__global__ void k_mc_init_conf(const McParams mc, unsigned N, unsigned words, uint64_t* __restrict__ conf_out) {
+    const unsigned chain = blockIdx.x * blockDim.x + threadIdx.x;
+    if(chain >= mc.num_chains_local) return;
+    const unsigned tag_init = (mc.call << 1) | 0u;
+    uint32_t r[4];
+    for(unsigned w = 0; w < words; w++) {
+        philox4x32_10(w, 0u, mc.chain0 + chain, tag_init, mc.seed_lo, mc.seed_hi, r);
+        uint64_t c = (uint64_t)r[0] | ((uint64_t)r[1] << 32);
+        if(w == words - 1u && (N & 63u)) c &= (1ull << (N & 63u)) - 1ull;
+        conf_out[(size_t)chain * words + w] = c;
+    }
+}
+
 // Wp: W with rows padded to Mp = 32*K complex (zeros beyond M) so that the hot loop has no bounds checks and one
 // base address per proposal: lane l reads Wp[site][l + 32k], k < K (coalesced 512 B per k).
 template<int K, int WORDS, bool FW_REAL, int MINB>
@@ -148,22 +165,30 @@ k_mc_rbm(const RbmDev psi, const cplx* __restrict__ Wp, const McParams mc, uint6
 
     uint32_t r[4];
     uint64_t conf[MAXW] = {0ull, 0ull, 0ull, 0ull};
-    #pragma unroll
-    for(int w = 0; w < WORDS; w++) {
-        philox4x32_10((uint32_t)w, 0u, gchain, tag_init, mc.seed_lo, mc.seed_hi, r);
-        conf[w] = (uint64_t)r[0] | ((uint64_t)r[1] << 32);
-    }
-    if(N & 63u) conf[WORDS - 1] &= (1ull << (N & 63u)) - 1ull;
-    // (the host dispatches WORDS == words_for(N), so the last word is the one to mask)
-
     // units beyond M hold theta = 0 (Wp is zero-padded), for which lc0 = 0
     cplx th[K];
-    #pragma unroll
-    for(int k = 0; k < K; k++) th[k] = cplx(0.0, 0.0);
-    for(unsigned i = 0; i < N; i++) {
-        const double s = conf_spin_t<WORDS>(conf, i);
+    if(angles_out) {
+        // the initial configuration and theta_0 = sigma_0 W were left in this chain's first sample slot by k_mc_init_conf
+        // and the tensor-core angle GEMM
         #pragma unroll
-        for(int k = 0; k < K; k++) th[k] += s * ldg(&Wl[(size_t)i * Mp + 32u * k]);
+        for(int w = 0; w < WORDS; w++) conf[w] = conf_out[(size_t)chain * WORDS + w];
+        #pragma unroll
+        for(int k = 0; k < K; k++) { const unsigned j = lane + 32u * k; th[k] = (j < M) ? angles_out[(size_t)chain * M + j] : cplx(0.0, 0.0); }
+    } else {
+        #pragma unroll
+        for(int w = 0; w < WORDS; w++) {
+            philox4x32_10((uint32_t)w, 0u, gchain, tag_init, mc.seed_lo, mc.seed_hi, r);
+            conf[w] = (uint64_t)r[0] | ((uint64_t)r[1] << 32);
+        }
+        if(N & 63u) conf[WORDS - 1] &= (1ull << (N & 63u)) - 1ull;
+        // (the host dispatches WORDS == words_for(N), so the last word is the one to mask)
+        #pragma unroll
+        for(int k = 0; k < K; k++) th[k] = cplx(0.0, 0.0);
+        for(unsigned i = 0; i < N; i++) {
+            const double s = conf_spin_t<WORDS>(conf, i);
+            #pragma unroll
+            for(int k = 0; k < K; k++) th[k] += s * ldg(&Wl[(size_t)i * Mp + 32u * k]);
+        }
     }
     auto re_log_psi = [&]() -> double {
         if(FW_REAL) {
@@ -258,21 +283,30 @@ k_mc_rbm_block(const RbmDev psi, const cplx* __restrict__ Wp, const McParams mc,
 
     uint32_t r[4];
     uint64_t conf[MAXW] = {0ull, 0ull, 0ull, 0ull};
-    #pragma unroll
-    for(unsigned w = 0; w < (unsigned)MAXW; w++) {
-        if(w < psi.words) {
-            philox4x32_10(w, 0u, gchain, tag_init, mc.seed_lo, mc.seed_hi, r);
-            conf[w] = (uint64_t)r[0] | ((uint64_t)r[1] << 32);
-            if(w == psi.words - 1u && (N & 63u)) conf[w] &= (1ull << (N & 63u)) - 1ull;
-        }
-    }
     cplx th[K];
-    #pragma unroll
-    for(int k = 0; k < K; k++) th[k] = cplx(0.0, 0.0);
-    for(unsigned i = 0; i < N; i++) {
-        const double s = conf_spin(conf, i);
+    if(angles_out) {
+        // initial configuration and theta_0 from this chain's first sample slot (k_mc_init_conf + the angle GEMM)
         #pragma unroll
-        for(int k = 0; k < K; k++) th[k] += s * ldg(&Wl[(size_t)i * Mp + (unsigned)MC_BLOCK_T * k]);
+        for(unsigned w = 0; w < (unsigned)MAXW; w++) if(w < psi.words) conf[w] = conf_out[(size_t)chain * psi.words + w];
+        #pragma unroll
+        for(int k = 0; k < K; k++) { const unsigned j = tid + (unsigned)MC_BLOCK_T * k; th[k] = (j < M) ? angles_out[(size_t)chain * M + j] : cplx(0.0, 0.0); }
+        __syncthreads();                                    // every thread has read the slot before thread 0 may overwrite it
+    } else {
+        #pragma unroll
+        for(unsigned w = 0; w < (unsigned)MAXW; w++) {
+            if(w < psi.words) {
+                philox4x32_10(w, 0u, gchain, tag_init, mc.seed_lo, mc.seed_hi, r);
+                conf[w] = (uint64_t)r[0] | ((uint64_t)r[1] << 32);
+                if(w == psi.words - 1u && (N & 63u)) conf[w] &= (1ull << (N & 63u)) - 1ull;
+            }
+        }
+        #pragma unroll
+        for(int k = 0; k < K; k++) th[k] = cplx(0.0, 0.0);
+        for(unsigned i = 0; i < N; i++) {
+            const double s = conf_spin(conf, i);
+            #pragma unroll
+            for(int k = 0; k < K; k++) th[k] += s * ldg(&Wl[(size_t)i * Mp + (unsigned)MC_BLOCK_T * k]);
+        }
     }
     unsigned buf = 0;
     // block-wide sum of one complex per thread, identical on every thread (fixed order), ONE barrier
@@ -383,6 +417,85 @@ __global__ void k_rbm_angles(const RbmDev psi, const uint64_t* __restrict__ conf
             if(log_psi_out) log_psi_out[s] = lp;
             if(weight_out) weight_out[s] = exp(2.0 * lp.re);
         }
+    }
+}
+
+// The batched initial-angle GEMM on the FP64 tensor cores:  theta [ns][M] = sigma [ns][N] . W [N][M]  (PsiRBM.hpp:71-80 for
+// every configuration at once), W viewed as a real [N][2M] matrix ((re, im) adjacent) so that the +-1 operand stays real and
+// each lane of an m8n8k4 tile ends up with one complex angle.  8 samples per warp, AG_CB real columns per pass, W streamed
+// through a cp.async double buffer of 32 sites; the +-1 operand comes from the configuration bits in registers.
+// Epilogue per sample: angles (optional), log psi = lp + fw sum_j lc0(theta_j), ExactSummation weight exp(2 Re log psi).
+// Products with +-1 are exact and the accumulation is fp64, so the result differs from the sequential sum only by the
+// order of the N additions (<= N ulp).
+constexpr int AG_KC = 32, AG_PAD = 8;
+constexpr size_t ag_smem(int cb) { return 2 * (size_t)AG_KC * (cb + AG_PAD) * sizeof(double); }
+template<int RW, int AG_CB>
+__global__ void __launch_bounds__(RW * 32) k_rbm_angles_dmma(const RbmDev psi, const uint64_t* __restrict__ confs, size_t ns,
+        cplx* __restrict__ angles_out, cplx* __restrict__ log_psi_out, double* __restrict__ weight_out) {
+    extern __shared__ __align__(16) double ag_buf[];
+    constexpr int STRIDE = AG_CB + AG_PAD, STAGE = AG_KC * STRIDE;
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u, row = lane >> 2, kq = lane & 3u;
+    const unsigned N = psi.N, M = psi.M, words = psi.words;
+    const size_t s = (size_t)blockIdx.x * (RW * 8) + warp * 8u + row;          // this lane's sample (A row / C row)
+    uint64_t cw[MAXW] = {0ull, 0ull, 0ull, 0ull};
+    #pragma unroll
+    for(unsigned w = 0; w < (unsigned)MAXW; w++) if(s < ns && w < words) cw[w] = confs[s * words + w];
+    const double* __restrict__ wr = reinterpret_cast<const double*>(psi.W);
+    const unsigned ncol = 2u * M;
+    const unsigned nkc = (N + AG_KC - 1) / AG_KC, ncb = (ncol + AG_CB - 1) / AG_CB, nstage = nkc * ncb;
+    auto issue = [&](unsigned q) {
+        double* dst = ag_buf + (q & 1u) * STAGE;
+        const unsigned cb = (q / nkc) * AG_CB, i0 = (q % nkc) * AG_KC;
+        for(unsigned e = threadIdx.x; e < AG_KC * (AG_CB / 2); e += RW * 32) {
+            const unsigned kk = e / (AG_CB / 2), c = (e % (AG_CB / 2)) * 2u;
+            const bool ok = (i0 + kk < N) && (cb + c < ncol);
+            cp_async16_zfill(dst + kk * STRIDE + c, ok ? (const void*)(wr + (size_t)(i0 + kk) * ncol + cb + c) : (const void*)wr, ok);
+        }
+        cp_async_commit();
+    };
+    cplx p(0.0, 0.0);
+    double acc[AG_CB / 8][2];
+    #pragma unroll
+    for(int t = 0; t < AG_CB / 8; t++) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+    issue(0);
+    for(unsigned q = 0; q < nstage; q++) {
+        if(q + 1u < nstage) { issue(q + 1u); cp_async_wait<1>(); } else cp_async_wait<0>();
+        __syncthreads();
+        const double* Ws = ag_buf + (q & 1u) * STAGE;
+        const unsigned cb = (q / nkc) * AG_CB, i0 = (q % nkc) * AG_KC;
+        #pragma unroll 2
+        for(unsigned k4 = 0; k4 < AG_KC / 4; k4++) {
+            const unsigned i = i0 + k4 * 4u + kq;
+            const unsigned wd = i >> 6;
+            uint64_t word = cw[0];
+            if(wd == 1u) word = cw[1];
+            if(wd == 2u) word = cw[2];
+            if(wd == 3u) word = cw[3];
+            const double asg = (s < ns && i < N) ? (((word >> (i & 63u)) & 1ull) ? 1.0 : -1.0) : 0.0;
+            const double* wrow = Ws + (k4 * 4u + kq) * STRIDE + row;
+            #pragma unroll
+            for(int t = 0; t < AG_CB / 8; t++) dmma(acc[t][0], acc[t][1], asg, wrow[t * 8]);
+        }
+        if(q % nkc == nkc - 1u) {                          // column block complete: these AG_CB / 2 angles of the 8 samples are final
+            #pragma unroll
+            for(int t = 0; t < AG_CB / 8; t++) {
+                const unsigned j = (cb >> 1) + (unsigned)t * 4u + kq;
+                if(s < ns && j < M) {
+                    const cplx th(acc[t][0], acc[t][1]);
+                    if(angles_out) angles_out[s * M + j] = th;
+                    p += lc0(th);
+                }
+                acc[t][0] = 0.0; acc[t][1] = 0.0;
+            }
+        }
+        __syncthreads();                                   // the buffer is refilled by the next iteration's issue
+    }
+    p.re += __shfl_xor_sync(FULL, p.re, 1); p.im += __shfl_xor_sync(FULL, p.im, 1);
+    p.re += __shfl_xor_sync(FULL, p.re, 2); p.im += __shfl_xor_sync(FULL, p.im, 2);
+    if(kq == 0 && s < ns) {
+        const cplx lp = psi.lp + psi.fw * p;
+        if(log_psi_out) log_psi_out[s] = lp;
+        if(weight_out) weight_out[s] = exp(2.0 * lp.re);
     }
 }
 

@@ -1,5 +1,6 @@
 // Ensembles, reductions over samples, ExpectationValue / TDVP, S.v, CG and dense solve.
 #include "vmc.hpp"
+#include "dmma.cuh"
 #include <cusolverDn.h>
 #include <string>
 #include <vector>
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(128) k_col_reduce_rbm(const uint64_t* __restri
     __shared__ __align__(16) double sgn[RBM_TS][RBM_IT];
     __shared__ cplx swx[RBM_TS];
     __shared__ double sw[RBM_TS];
-    const unsigned j = blockIdx.x * 128u + threadIdx.x;
+    const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;       // blockDim.x = 32 .. 128 (narrow models: no idle threads)
     const unsigned i0 = blockIdx.y * RBM_IT;
     const size_t s0 = (size_t)blockIdx.z * chunk, s1 = min(ns, s0 + chunk);
     const bool jok = j < M;
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(128) k_col_reduce_rbm(const uint64_t* __restri
     const unsigned word = i0 >> 6, shift = i0 & 63u;     // RBM_IT divides 64: the sites of a tile share one word
     for(size_t sb = s0; sb < s1; sb += RBM_TS) {
         __syncthreads();
-        for(unsigned e = threadIdx.x; e < RBM_TS * RBM_IT; e += 128u) {
+        for(unsigned e = threadIdx.x; e < RBM_TS * RBM_IT; e += blockDim.x) {
             const unsigned st = e / RBM_IT, ii = e % RBM_IT;
             const size_t s = sb + st;
             double sg = 0.0;
@@ -169,6 +170,28 @@ __global__ void k_sum_chunks(const cplx* __restrict__ part, unsigned chunks, siz
         out[k] = conj_out ? conj(a) : a;
     }
 }
+// The same sums for MANY chunks of a SHORT vector (C1: 512 chunks of P = 512): 32 columns x 32 chunk groups per block; group
+// g adds the chunks g, g + 32, ... and the 32 group sums are added in fixed order.  Up to two vectors per launch.
+__global__ void __launch_bounds__(1024) k_sum_chunks_wide(const cplx* __restrict__ part_a, const cplx* __restrict__ part_b, unsigned chunks, size_t P,
+                                                          cplx* __restrict__ out_a, cplx* __restrict__ out_b, bool conj_b) {
+    __shared__ cplx sm[32][33];
+    const unsigned col = threadIdx.x & 31u, g = threadIdx.x >> 5;
+    const size_t k = (size_t)blockIdx.x * 32u + col;
+    const cplx* __restrict__ part = blockIdx.y ? part_b : part_a;
+    cplx a(0.0, 0.0);
+    if(k < P) for(unsigned c = g; c < chunks; c += 32u) a += part[(size_t)c * P + k];
+    sm[g][col] = a;
+    __syncthreads();
+    if(g == 0 && k < P) {
+        cplx t(0.0, 0.0);
+        #pragma unroll 8
+        for(int q = 0; q < 32; q++) t += sm[q][col];
+        if(blockIdx.y) out_b[k] = conj_b ? conj(t) : t; else out_a[k] = t;
+    }
+}
+// out_a (and out_b) = chunk sums, picking the launch shape by the number of chunks
+static void sum_chunks(const cplx* part_a, cplx* out_a, const cplx* part_b, cplx* out_b, unsigned chunks, size_t P, bool conj_b = false);
+
 __global__ void k_fill_cplx(cplx* p, cplx v, size_t n) {
     for(size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) p[k] = v;
 }
@@ -279,21 +302,8 @@ __global__ void __launch_bounds__(256) k_rowdot_rbm(const uint64_t* __restrict__
 // generated from the configuration bits in registers, the other operand is staged in shared memory.
 // Fragment layout (PTX ISA, m8n8k4 .f64): A[row = lane>>2][k = lane&3], B[k = lane&3][col = lane>>2],
 // C/D[row = lane>>2][col = 2*(lane&3) + {0,1}]  =>  each lane ends up with ONE complex number per 8x8 tile.
-__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
-__device__ __forceinline__ double bit_sign(const uint64_t* cw, unsigned i) { return ((cw[i >> 6] >> (i & 63u)) & 1ull) ? 1.0 : -1.0; }
-
 constexpr int RD_KC = 32, RD_PAD = 8;                                  // 8 samples per warp, RD_CB real columns per pass
 constexpr size_t rd_smem(int cb) { return 2 * (size_t)RD_KC * (cb + RD_PAD) * sizeof(double); }   // double-buffered V tile (cp.async)
-
-__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool valid) {
-    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
-    const int bytes = valid ? 16 : 0;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gsrc), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template<int N_> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
 
 template<int RW, int RD_CB>                               // warps per block (8 samples each); real columns per pass (64 | 128)
 __global__ void __launch_bounds__(RW * 32) k_rowdot_dmma(const uint64_t* __restrict__ conf, const cplx* __restrict__ T,
@@ -844,6 +854,16 @@ __global__ void k_sum_rows(const cplx* __restrict__ O, size_t ns, unsigned P, cp
 static inline unsigned grid_for(size_t n, unsigned block = 256) {
     return (unsigned)std::max<size_t>(1, std::min<size_t>((n + block - 1) / block, (size_t)ctx().num_sms * 32));
 }
+static void sum_chunks(const cplx* part_a, cplx* out_a, const cplx* part_b, cplx* out_b, unsigned chunks, size_t P, bool conj_b) {
+    if(chunks >= 32u && (P + 255) / 256 < (size_t)ctx().num_sms) {
+        k_sum_chunks_wide<<<dim3((unsigned)((P + 31) / 32), part_b ? 2 : 1), 1024, 0, stream()>>>(part_a, part_b, chunks, P, out_a, out_b, conj_b);
+        ANGPU_CHECK_LAUNCH(); count_launch();
+        return;
+    }
+    k_sum_chunks<<<grid_for(P), 256, 0, stream()>>>(part_a, chunks, P, out_a);
+    if(part_b) k_sum_chunks<<<grid_for(P), 256, 0, stream()>>>(part_b, chunks, P, out_b, conj_b);
+    ANGPU_CHECK_LAUNCH(); count_launch(part_b ? 2 : 1);
+}
 
 // ============================================================================================ Ensemble
 
@@ -972,7 +992,8 @@ static ColPartials col_reduce_partials(TDVP& t, const cplx* X, bool want_mean) {
     }
     unsigned chunks; size_t chunk;
     if(t.factorised) {
-        const unsigned jb = ceil_div(t.rbm_M, 128), ib = ceil_div(t.rbm_N, RBM_IT);
+        const unsigned jt = std::min(128u, (t.rbm_M + 31u) / 32u * 32u);      // threads per block of k_col_reduce_rbm
+        const unsigned jb = ceil_div(t.rbm_M, jt), ib = ceil_div(t.rbm_N, RBM_IT);
         // chunks of whole 32-sample tiles: enough blocks to fill the GPU twice, but the partial-sum traffic
         // (chunks * P * 16 B written and read back) is kept below ~64 MB and chunks <= 64
         const size_t colblocks = (2 * (size_t)t.rbm_M + 63) / 64;     // k_colreduce_dmma blocks per chunk
@@ -994,7 +1015,7 @@ static ColPartials col_reduce_partials(TDVP& t, const cplx* X, bool want_mean) {
         chunk = ((ns + chunks - 1) / chunks + RBM_TS - 1) / RBM_TS * RBM_TS; chunks = (unsigned)((ns + chunk - 1) / chunk);
         t.chunk_buf.resize((size_t)2 * chunks * P);
         cplx* pm = want_mean ? t.chunk_buf.p : nullptr; cplx* px = t.chunk_buf.p + (size_t)chunks * P;
-        if(want_mean) k_col_reduce_rbm<true><<<dim3(jb, ib, chunks), 128, 0, stream()>>>(t.S.conf.p, t.T.p, t.S.weight.p, X, ns, t.rbm_N, t.rbm_M, t.words, chunk, pm, px);
+        if(want_mean) k_col_reduce_rbm<true><<<dim3(jb, ib, chunks), jt, 0, stream()>>>(t.S.conf.p, t.T.p, t.S.weight.p, X, ns, t.rbm_N, t.rbm_M, t.words, chunk, pm, px);
         else if(use_dmma()) {
             const dim3 g128(ceil_div(2 * t.rbm_M, 128), chunks), g64(ceil_div(2 * t.rbm_M, 64), chunks);
             if(t.rbm_N <= 64u) k_colreduce_dmma<1, 64><<<g64, CD_WARPS * 32, 0, stream()>>>(t.S.conf.p, t.T.p, t.S.weight.p, X, ns, t.rbm_N, t.rbm_M, t.words, chunk, px);
@@ -1006,7 +1027,7 @@ static ColPartials col_reduce_partials(TDVP& t, const cplx* X, bool want_mean) {
                 k_colreduce_dmma<2, 64><<<g64z, CD_WARPS * 32, 0, stream()>>>(t.S.conf.p, t.T.p, t.S.weight.p, X, ns, t.rbm_N, t.rbm_M, t.words, chunk, px);
             }
         }
-        else k_col_reduce_rbm<false><<<dim3(jb, ib, chunks), 128, 0, stream()>>>(t.S.conf.p, t.T.p, t.S.weight.p, X, ns, t.rbm_N, t.rbm_M, t.words, chunk, pm, px);
+        else k_col_reduce_rbm<false><<<dim3(jb, ib, chunks), jt, 0, stream()>>>(t.S.conf.p, t.T.p, t.S.weight.p, X, ns, t.rbm_N, t.rbm_M, t.words, chunk, pm, px);
         ANGPU_CHECK_LAUNCH(); count_launch();
         return ColPartials{chunks, pm, px};
     }
@@ -1036,9 +1057,7 @@ static void col_reduce(TDVP& t, const cplx* X, cplx* mean_out, cplx* x_out) {
         return;
     }
     const ColPartials cp = col_reduce_partials(t, X, mean_out != nullptr);
-    if(mean_out) { k_sum_chunks<<<grid_for(t.P), 256, 0, stream()>>>(cp.mean, cp.chunks, t.P, mean_out); ANGPU_CHECK_LAUNCH(); count_launch(); }
-    k_sum_chunks<<<grid_for(t.P), 256, 0, stream()>>>(cp.x, cp.chunks, t.P, x_out);
-    ANGPU_CHECK_LAUNCH(); count_launch();
+    sum_chunks(cp.x, x_out, mean_out ? cp.mean : nullptr, mean_out, cp.chunks, t.P);
 }
 
 void TDVP::mark(int i) {
