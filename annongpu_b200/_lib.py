@@ -113,6 +113,7 @@ _SIGNATURES = {
     "angpu_tdvp_solve_cg": [vp, dbl, u32, dbl, dbl, vp, vp, vp, vp],
     "angpu_tdvp_solve_dense": [vp, dbl, dbl, vp, vp],
     "angpu_tdvp_apply_update": [vp, vp, vp],
+    "angpu_hpd_solve": [u32, vp, vp, vp],
     "angpu_tdvp_build_S_tensorcore": [vp],
     "angpu_tdvp_set_profile": [vp, i32],
     "angpu_tdvp_phase_ms": [vp, vp],

@@ -31,7 +31,7 @@ __all__ = [
     "log_psi_s", "psi_O_k", "psi_O_k_vector", "log_psi", "psi_vector", "log_psi_vector", "apply_operator",
     "local_energies", "activation_function", "pauli_apply", "setDevice", "start_profiling", "stop_profiling",
     "synchronize", "launch_count", "set_stream", "measure_fp64_tflops", "AngpuError",
-    "comm_unique_id", "comm_init", "comm_destroy", "comm_rank",
+    "comm_unique_id", "comm_init", "comm_destroy", "comm_rank", "hpd_solve",
 ]
 AngpuError = _lib.AngpuError
 
@@ -1027,6 +1027,16 @@ def set_allreduce(fn):
 
     _allreduce_cb = ALLREDUCE_FN(trampoline)
     lib.angpu_set_allreduce(_allreduce_cb, None)
+
+
+def hpd_solve(A, b):
+    """x = A^{-1} b for a Hermitian positive definite A on the device: the hand-written blocked Cholesky behind TDVP.solve."""
+    A = _c128(A)
+    b = _c128(b).ravel()
+    assert A.ndim == 2 and A.shape[0] == A.shape[1] == b.size
+    x = np.empty(b.size, dtype=np.complex128)
+    call("angpu_hpd_solve", b.size, _p(A), _p(b), _p(x))
+    return x
 
 
 def comm_unique_id():

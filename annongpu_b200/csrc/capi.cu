@@ -388,6 +388,17 @@ int angpu_measure_fp64_tflops(double* out) { API_BEGIN NOTNULL(out); *out = meas
 int angpu_tdvp_solve_dense(angpu_tdvp_t tdvp, double shift_abs, double shift_rel, const double rhs_phase[2], double* x_out) {
     API_BEGIN NOTNULL(tdvp); NOTNULL(rhs_phase); tdvp->t->solve_dense(shift_abs, shift_rel, c2(rhs_phase), cp(x_out)); API_END
 }
+int angpu_hpd_solve(unsigned n, const double* A, const double* b, double* x_out) {
+    API_BEGIN NOTNULL(A); NOTNULL(b); NOTNULL(x_out);
+    ANGPU_REQUIRE(n >= 1, "angpu_hpd_solve: n >= 1");
+    DevBuf<cplx> dA, db; DevBuf<int> info(2);
+    dA.upload(cp(A), (size_t)n * n); db.upload(cp(b), n);
+    cholesky_solve(dA.p, db.p, n, info.p);
+    int hinfo = 0; info.download(&hinfo, 1);
+    if(hinfo != 0) throw Error("angpu_hpd_solve: the matrix is not positive definite (pivot " + std::to_string(hinfo) + ")");
+    db.download(cp(x_out), n);
+    API_END
+}
 int angpu_tdvp_apply_update(angpu_tdvp_t tdvp, angpu_psi_t psi, const double alpha[2]) {
     API_BEGIN NOTNULL(tdvp); NOTNULL(psi); NOTNULL(alpha);
     ANGPU_REQUIRE(tdvp->t->last_x != nullptr, "TDVP: no solution on the device (call solve_cg / solve_dense first)");

@@ -1,7 +1,7 @@
 // Ensembles, reductions over samples, ExpectationValue / TDVP, S.v, CG and dense solve.
 #include "vmc.hpp"
 #include "dmma.cuh"
-#include <cusolverDn.h>
+#include "zherk_dmma.cuh"
 #include <string>
 #include <vector>
 #include <algorithm>
@@ -368,96 +368,6 @@ __global__ void __launch_bounds__(RW * 32) k_rowdot_dmma(const uint64_t* __restr
     tot.re += __shfl_xor_sync(FULL, tot.re, 1); tot.im += __shfl_xor_sync(FULL, tot.im, 1);
     tot.re += __shfl_xor_sync(FULL, tot.re, 2); tot.im += __shfl_xor_sync(FULL, tot.im, 2);
     if(kq == 0 && s < ns) a_out[s] = tot;
-}
-
-// ---- exact fp64 S build on the FP64 tensor cores.  S'[k][k'] = sum_s w_s conj(O_sk) O_sk' is read off the REAL Gram matrix
-// G = X^T diag(w) X of X = O viewed as [ns][2P] doubles ((re, im) adjacent):
-//     Re S'[k][k'] = G[2k][2k'] + G[2k+1][2k'+1],   Im S'[k][k'] = G[2k][2k'+1] - G[2k+1][2k']
-// (4 ns P^2 flops over the upper-triangular tiles, the same count as the complex Hermitian update).  Block = one 128 x 128
-// real tile (64 x 64 complex), 8 warps as 4 x 2, warp tile 32 x 64 = 4 x 8 mma.m8n8k4.f64 tiles with accumulators in
-// registers; both operand tiles stream through a cp.async double buffer of 32 samples; 12 LDS.64 feed 32 DMMAs per k-step.
-constexpr int ZD_T = 128, ZD_KT = 32, ZD_PAD = 8, ZD_STRIDE = ZD_T + ZD_PAD;
-constexpr int ZD_TILE_DOUBLES = ZD_KT * ZD_STRIDE;
-constexpr size_t ZD_SMEM = (size_t)(4 * ZD_TILE_DOUBLES + 2 * ZD_KT) * sizeof(double);      // 2 stages x (A, B tile) + weights
-template<int NWN>                                         // warps along n: 2 (8 warps, warp tile 32 x 64) or 4 (16 warps, 32 x 32)
-__global__ void __launch_bounds__(128 * NWN) k_zherk_dmma(const cplx* __restrict__ O, const double* __restrict__ w, size_t ns, unsigned P,
-                                                    size_t chunk, cplx* __restrict__ Sout, size_t split_stride) {
-    extern __shared__ __align__(16) double zd_smem[];
-    const unsigned nt = (P + 63u) / 64u;
-    unsigned t = blockIdx.x, tr = 0;
-    while(t >= nt - tr) { t -= nt - tr; tr++; }
-    const unsigned tc = tr + t;
-    const size_t s0 = (size_t)blockIdx.y * chunk, s1 = min(ns, s0 + chunk);
-    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u, row = lane >> 2, kq = lane & 3u;
-    constexpr int NB = 8 / (NWN / 2);                          // n-tiles per warp: 8 or 4
-    constexpr unsigned NT = 128u * NWN;                        // threads per block
-    const unsigned m0 = (warp / NWN) * 32u, n0 = (warp % NWN) * (8u * NB);
-    const double* __restrict__ X = reinterpret_cast<const double*>(O);
-    const unsigned ncol = 2u * P, ca = tr * ZD_T, cb = tc * ZD_T;
-    const bool diag = (tr == tc);
-    double* wsm = zd_smem + 4 * ZD_TILE_DOUBLES;
-    auto issue = [&](size_t sb, unsigned buf) {
-        double* Ta = zd_smem + (size_t)buf * 2 * ZD_TILE_DOUBLES;
-        double* Tb = Ta + ZD_TILE_DOUBLES;
-        for(unsigned e = threadIdx.x; e < ZD_KT * (ZD_T / 2); e += NT) {
-            const unsigned kk = e / (ZD_T / 2), c = (e % (ZD_T / 2)) * 2u;
-            const size_t sidx = sb + kk;
-            const bool oka = sidx < s1 && ca + c < ncol, okb = sidx < s1 && cb + c < ncol;
-            cp_async16_zfill(Ta + kk * ZD_STRIDE + c, oka ? (const void*)(X + sidx * ncol + ca + c) : (const void*)X, oka);
-            if(!diag) cp_async16_zfill(Tb + kk * ZD_STRIDE + c, okb ? (const void*)(X + sidx * ncol + cb + c) : (const void*)X, okb);
-        }
-        if(threadIdx.x < ZD_KT) { const size_t sidx = sb + threadIdx.x; wsm[buf * ZD_KT + threadIdx.x] = sidx < s1 ? w[sidx] : 0.0; }
-        cp_async_commit();
-    };
-    double acc[4][NB][2];
-    #pragma unroll
-    for(int a = 0; a < 4; a++)
-        #pragma unroll
-        for(int b = 0; b < NB; b++) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
-    unsigned buf = 0;
-    if(s0 < s1) issue(s0, 0);
-    for(size_t sb = s0; sb < s1; sb += ZD_KT, buf ^= 1u) {
-        if(sb + ZD_KT < s1) { issue(sb + ZD_KT, buf ^ 1u); cp_async_wait<1>(); } else cp_async_wait<0>();
-        __syncthreads();
-        const double* Ta = zd_smem + (size_t)buf * 2 * ZD_TILE_DOUBLES;
-        const double* Tb = diag ? Ta : Ta + ZD_TILE_DOUBLES;
-        const double* wk = wsm + buf * ZD_KT;
-        #pragma unroll 2
-        for(unsigned k4 = 0; k4 < ZD_KT / 4; k4++) {
-            const unsigned kk = k4 * 4u + kq;
-            const double wv = wk[kk];
-            const double* ra = Ta + kk * ZD_STRIDE + m0 + row;
-            const double* rb = Tb + kk * ZD_STRIDE + n0 + row;
-            double af[4], bf[NB];
-            #pragma unroll
-            for(int a = 0; a < 4; a++) af[a] = wv * ra[a * 8];
-            #pragma unroll
-            for(int b = 0; b < NB; b++) bf[b] = rb[b * 8];
-            #pragma unroll
-            for(int a = 0; a < 4; a++)
-                #pragma unroll
-                for(int b = 0; b < NB; b++) dmma(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
-        }
-        __syncthreads();                                   // the buffer is refilled by the next iteration's issue
-    }
-    // epilogue: lane (row r, kq) holds G[R][C], G[R][C+1] with R = m0 + 8a + r, C = n0 + 8b + 2 kq; the odd row R+1 lives in
-    // lane ^ 4.  Even-row lanes combine the 2 x 2 real block into one complex entry and write it (and its mirror).
-    cplx* Sp = Sout + (size_t)blockIdx.y * split_stride;
-    #pragma unroll
-    for(int a = 0; a < 4; a++)
-        #pragma unroll
-        for(int b = 0; b < NB; b++) {
-            const double p0 = __shfl_xor_sync(FULL, acc[a][b][0], 4), p1 = __shfl_xor_sync(FULL, acc[a][b][1], 4);
-            if((row & 1u) == 0u) {
-                const unsigned k = tr * 64u + (m0 + 8u * a + row) / 2u, kp = tc * 64u + (n0 + 8u * b) / 2u + kq;
-                if(k < P && kp < P && (!diag || kp >= k)) {        // diagonal tiles: upper part + mirror, exactly Hermitian
-                    cplx v(acc[a][b][0] + p1, acc[a][b][1] - p0);
-                    if(k == kp) v.im = 0.0;
-                    Sp[(size_t)k * P + kp] = v;
-                    if(k != kp) Sp[(size_t)kp * P + k] = conj(v);
-                }
-            }
-        }
 }
 
 constexpr int CD_WARPS = 8, CD_KT = 32, CD_PAD = 8;   // tiles of 32 samples x CD_CB real columns
@@ -1149,12 +1059,12 @@ void TDVP::build_S() {
         else {
             static bool attr_set = false;
             if(!attr_set) {
-                ANGPU_CUDA(cudaFuncSetAttribute(k_zherk_dmma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZD_SMEM));
-                ANGPU_CUDA(cudaFuncSetAttribute(k_zherk_dmma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZD_SMEM));
+                ANGPU_CUDA(cudaFuncSetAttribute(k_zherk_dmma<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZD_SMEM));
+                ANGPU_CUDA(cudaFuncSetAttribute(k_zherk_dmma<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZD_SMEM));
                 attr_set = true;
             }
-            if(env && std::string(env) == "dmma8") k_zherk_dmma<2><<<dim3(tiles, splits), 256, ZD_SMEM, stream()>>>(O.p, S.weight.p, ns, P, chunk, part, stride);
-            else k_zherk_dmma<4><<<dim3(tiles, splits), 512, ZD_SMEM, stream()>>>(O.p, S.weight.p, ns, P, chunk, part, stride);
+            if(env && std::string(env) == "dmma8") k_zherk_dmma<2, false><<<dim3(tiles, splits), 256, ZD_SMEM, stream()>>>(reinterpret_cast<const double*>(O.p), 2 * (size_t)P, S.weight.p, ns, P, chunk, part, P, stride);
+            else k_zherk_dmma<4, false><<<dim3(tiles, splits), 512, ZD_SMEM, stream()>>>(reinterpret_cast<const double*>(O.p), 2 * (size_t)P, S.weight.p, ns, P, chunk, part, P, stride);
         }
         ANGPU_CHECK_LAUNCH(); count_launch();
     } else Smat.zero();
@@ -1349,7 +1259,6 @@ int TDVP::solve_cg(double tol, unsigned max_iter, double shift_abs, double shift
     return (int)it;
 }
 
-static cusolverDnHandle_t g_cusolver = nullptr;
 void TDVP::solve_dense(double shift_abs, double shift_rel, cplx rhs_phase, cplx* x_host) {
     ANGPU_REQUIRE(evaluated, "TDVP: call eval first");
     set_reduce(sharded);
@@ -1358,33 +1267,19 @@ void TDVP::solve_dense(double shift_abs, double shift_rel, cplx rhs_phase, cplx*
     const size_t n = P;
     DevBuf<double> dg;
     if(shift_rel != 0.0) tdvp_diag(*this, dg); else { dg.resize(n); dg.zero(); }
-    // row-major Hermitian S read as column-major is conj(S): solve conj(S) y = conj(b), x = conj(y).
-    // The factorisation workspace (a copy of S, 16 P^2 bytes) is a grow-only member: cudaMalloc/cudaFree of a GB-sized
-    // buffer per call cost 0.1-0.8 s on some boxes.
-    DevBuf<cplx>& A = solve_A; DevBuf<cplx>& b = solve_b; DevBuf<cplx>& work = solve_work; DevBuf<int>& info = solve_info;
-    b.resize(n);
+    // The factorisation works in place on a copy of S (16 P^2 bytes), a grow-only member: cudaMalloc/cudaFree of a GB-sized
+    // buffer per call cost 0.1-0.8 s on some boxes.  Hand-written blocked Cholesky on the row-major upper triangle
+    // (cholesky.cu): no library call on the SR path.
+    DevBuf<cplx>& A = solve_A; DevBuf<cplx>& b = solve_b; DevBuf<int>& info = solve_info;
+    b.resize(n); info.resize(2);
     A.copy_from(Smat);
     k_add_diag_shift<<<grid_for(n), 256, 0, stream()>>>(A.p, dg.p, shift_abs, shift_rel, P);
     k_scale_vec<<<grid_for(n), 256, 0, stream()>>>(F.p, rhs_phase, b.p, n, false);
-    k_conj_inplace<<<grid_for(n), 256, 0, stream()>>>(b.p, n);
-    ANGPU_CHECK_LAUNCH(); count_launch(3);
-    if(!g_cusolver) { if(cusolverDnCreate(&g_cusolver) != CUSOLVER_STATUS_SUCCESS) throw Error("cusolverDnCreate failed"); }
-    cusolverDnSetStream(g_cusolver, stream());
-    auto* Ad = reinterpret_cast<cuDoubleComplex*>(A.p); auto* bd = reinterpret_cast<cuDoubleComplex*>(b.p);
-    const int ni = (int)n;
-    // One Zpotrf over the whole matrix: measured 30.8 ms at P = 8384 on B200 (25.6 TFLOP/s, 70 % of the FP64 peak) once the
-    // handle and workspace exist (the first call costs 100-500 ms); a hand-blocked ZHERK/ZTRSM variant was slower (36 ms).
-    int lwork = 0;
-    if(cusolverDnZpotrf_bufferSize(g_cusolver, CUBLAS_FILL_MODE_LOWER, ni, Ad, ni, &lwork) != CUSOLVER_STATUS_SUCCESS) throw Error("Zpotrf_bufferSize failed");
-    work.resize((size_t)std::max(lwork, 1)); info.resize(2);
-    const int nblk = 1;
-    if(cusolverDnZpotrf(g_cusolver, CUBLAS_FILL_MODE_LOWER, ni, Ad, ni, reinterpret_cast<cuDoubleComplex*>(work.p), lwork, info.p) != CUSOLVER_STATUS_SUCCESS) throw Error("Zpotrf failed");
-    int hinfo = 0; info.download(&hinfo, 1);
-    if(hinfo != 0) throw Error("dense solve: S + shift is not positive definite (Zpotrf info = " + std::to_string(hinfo) + "); increase the diagonal shift");
-    if(cusolverDnZpotrs(g_cusolver, CUBLAS_FILL_MODE_LOWER, ni, 1, Ad, ni, bd, ni, info.p + nblk) != CUSOLVER_STATUS_SUCCESS) throw Error("Zpotrs failed");
-    k_conj_inplace<<<grid_for(n), 256, 0, stream()>>>(b.p, n);
-    ANGPU_CHECK_LAUNCH(); count_launch();
+    ANGPU_CHECK_LAUNCH(); count_launch(2);
+    cholesky_solve(A.p, b.p, P, info.p);
     mark(6);
+    int hinfo = 0; info.download(&hinfo, 1);
+    if(hinfo != 0) throw Error("dense solve: S + shift is not positive definite (pivot " + std::to_string(hinfo) + " is not positive); increase the diagonal shift");
     last_x = b.p;
     if(x_host) b.download(x_host, n); else ANGPU_CUDA(cudaStreamSynchronize(stream()));
     if(profile) ANGPU_CUDA(cudaEventElapsedTime(&phase_ms[5], ev[5], ev[6]));

@@ -208,6 +208,11 @@ int angpu_tdvp_apply_update(angpu_tdvp_t tdvp, angpu_psi_t psi, const double alp
  * TMEM; ~1e-5 relative to ||S||).  angpu_tdvp_eval itself builds S in exact fp64 (the reference: fp64 atomics, :216-279). */
 int angpu_tdvp_build_S_tensorcore(angpu_tdvp_t tdvp);
 
+/* The solver behind angpu_tdvp_solve_dense on caller-given data: x = A^{-1} b for a Hermitian positive definite A
+ * (n x n complex, row-major; only the upper triangle is read), blocked Cholesky + triangular solves on the device
+ * (csrc/cholesky.cu).  Fails when a pivot is not positive. */
+int angpu_hpd_solve(unsigned n, const double* A, const double* b, double* x_out);
+
 /* ---- measurement aids (no reference counterpart) -------------------------------------------------------- */
 /* CUDA-event timing on the library stream, ms: {sampling, E_loc, O_k + reductions, eval total} of the last eval / eval_F,
  * {S build, last solve_cg / solve_dense} */

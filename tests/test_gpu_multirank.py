@@ -78,3 +78,24 @@ def test_apply_update_on_device_matches_host_update(gpu):
     c0, l0 = gpu.MonteCarloSpins(256, 1, 2, 256, True, seed=5).sample(psi)
     c1, l1 = gpu.MonteCarloSpins(256, 1, 2, 256, True, seed=5).sample(fresh)
     assert np.array_equal(c0, c1) and np.abs(l0 - l1).max() <= 1e-13
+
+
+@pytest.mark.parametrize("n", [1, 7, 100, 128, 129, 300, 1000])
+def test_blocked_cholesky_solve_against_numpy(gpu, n):
+    """The hand-written dense solve (csrc/cholesky.cu) on random Hermitian positive definite systems whose sizes straddle the
+    128-row blocks and the 64-column tiles of the tensor-core trailing update: residual and solution against numpy."""
+    rng = np.random.default_rng(n)
+    B = rng.standard_normal((n, n + 5)) + 1j * rng.standard_normal((n, n + 5))
+    A = B @ B.conj().T / n + 0.05 * np.eye(n)
+    b = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    x = gpu.hpd_solve(A, b)
+    x_ref = np.linalg.solve(A, b)
+    assert np.linalg.norm(A @ x - b) <= 1e-11 * np.linalg.norm(b) * np.linalg.cond(A)
+    assert np.linalg.norm(x - x_ref) <= 1e-10 * np.linalg.norm(x_ref) * max(1.0, np.linalg.cond(A) / 100)
+    # only the upper triangle is read
+    A2 = A.copy()
+    A2[np.tril_indices(n, -1)] = 123.0
+    assert np.array_equal(gpu.hpd_solve(A2, b), x)
+    if n > 1:
+        with pytest.raises(gpu.AngpuError):
+            gpu.hpd_solve(A - 2.0 * np.trace(A).real / n * np.eye(n), b)
