@@ -1,4 +1,6 @@
 // Host-side wavefunction objects: parameter bookkeeping + kernel launches.
+#include <unordered_set>
+#include <mutex>
 #include "psi.hpp"
 #include "rbm_kernels.cuh"
 #include "rbm_sampler.cuh"
@@ -9,6 +11,16 @@
 #include <string>
 
 namespace angpu {
+
+bool Psi::registry(const Psi* p, int op) {
+    static std::mutex mu;
+    static std::unordered_set<const Psi*> live;
+    std::lock_guard<std::mutex> g(mu);
+    if(op > 0) { live.insert(p); return true; }
+    if(op < 0) { live.erase(p); return false; }
+    return live.count(p) != 0;
+}
+
 
 static Ctx g_ctx;
 Ctx& ctx() { return g_ctx; }

@@ -29,12 +29,20 @@ struct SampleSet {
 };
 
 struct Psi {
+  private:
+    static bool registry(const Psi* p, int op);     // +1 insert, -1 erase, 0 query (psi.cu)
+  public:
     enum Kind { RBM = 0, DEEP = 1, CNN = 2, CLASSICAL = 3 };
     Kind     kind;
     unsigned N = 0, words = 1, P = 0;
     cplx     lp{0.0, 0.0};
 
-    virtual ~Psi() {}
+    // live-object registry: TDVP / HilbertSpaceDistance / KullbackLeibler keep a Psi* for the lazily materialised dense O rows;
+    // a C-ABI caller may destroy the psi in between, which must surface as an error instead of a use-after-free
+    Psi() { registry(this, +1); }
+    Psi(const Psi& o) : kind(o.kind), N(o.N), words(o.words), P(o.P), lp(o.lp) { registry(this, +1); }
+    virtual ~Psi() { registry(this, -1); }
+    static bool is_live(const Psi* p) { return registry(p, 0); }
     virtual Psi* clone() const = 0;
     virtual void get_params(cplx* out) const = 0;
     virtual void set_params(const cplx* in) = 0;

@@ -1027,6 +1027,7 @@ void TDVP::weighted_conj_column_sums(const cplx* X, cplx* x_out) { col_reduce(*t
 void TDVP::ensure_dense_O(Psi* psi) {
     if(have_dense_O) return;
     ANGPU_REQUIRE(evaluated && psi, "TDVP: no samples (call eval first)");
+    ANGPU_REQUIRE(Psi::is_live(psi), "TDVP: the psi of the last eval was destroyed before its O_k rows were materialised (keep it alive until get_S / get_O_k_samples / solve_dense / build_S_tensorcore, or call them before angpu_psi_destroy)");
     O.resize(S.ns * (size_t)P);
     psi->ok_rows(S, 0, S.ns, O.p);
     have_dense_O = true;

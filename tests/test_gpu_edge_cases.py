@@ -133,3 +133,17 @@ def test_boundary_errors(gpu):
     t.eval(H, psi, gpu.ExactSummationSpins(8))
     with pytest.raises(RuntimeError, match="positive definite"):
         t.solve(shift_abs=-10.0, shift_rel=0.0)
+
+
+def test_destroyed_psi_is_an_error_not_a_use_after_free(gpu):
+    """TDVP materialises the dense O_k rows lazily from the psi of its last eval; a C-ABI caller that destroyed that psi
+    in between gets an error message (the Python wrapper normally keeps the psi alive through TDVP._keep)."""
+    spec = F.rbm_spec(8, 16, noise=5e-2, final_weight=3, seed=2)
+    psi = make_psi(gpu, spec)
+    H = make_op(gpu, F.heisenberg(8, F.ring_bonds(8)))
+    t = gpu.TDVP(psi.num_params, True)
+    t.eval_F(H, psi, gpu.ExactSummationSpins(8))
+    t._keep = None
+    psi.__del__()                                   # angpu_psi_destroy
+    with pytest.raises(RuntimeError, match="destroyed"):
+        t.O_k_samples
