@@ -391,9 +391,9 @@ int angpu_tdvp_solve_dense(angpu_tdvp_t tdvp, double shift_abs, double shift_rel
 int angpu_hpd_solve(unsigned n, const double* A, const double* b, double* x_out) {
     API_BEGIN NOTNULL(A); NOTNULL(b); NOTNULL(x_out);
     ANGPU_REQUIRE(n >= 1, "angpu_hpd_solve: n >= 1");
-    DevBuf<cplx> dA, db; DevBuf<int> info(2);
+    DevBuf<cplx> dA, db, work; DevBuf<int> info(2);
     dA.upload(cp(A), (size_t)n * n); db.upload(cp(b), n);
-    cholesky_solve(dA.p, db.p, n, info.p);
+    cholesky_solve(dA.p, db.p, n, info.p, work);
     int hinfo = 0; info.download(&hinfo, 1);
     if(hinfo != 0) throw Error("angpu_hpd_solve: the matrix is not positive definite (pivot " + std::to_string(hinfo) + ")");
     db.download(cp(x_out), n);

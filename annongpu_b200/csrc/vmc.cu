@@ -1277,7 +1277,7 @@ void TDVP::solve_dense(double shift_abs, double shift_rel, cplx rhs_phase, cplx*
     k_add_diag_shift<<<grid_for(n), 256, 0, stream()>>>(A.p, dg.p, shift_abs, shift_rel, P);
     k_scale_vec<<<grid_for(n), 256, 0, stream()>>>(F.p, rhs_phase, b.p, n, false);
     ANGPU_CHECK_LAUNCH(); count_launch(2);
-    cholesky_solve(A.p, b.p, P, info.p);
+    cholesky_solve(A.p, b.p, P, info.p, solve_work);
     mark(6);
     int hinfo = 0; info.download(&hinfo, 1);
     if(hinfo != 0) throw Error("dense solve: S + shift is not positive definite (pivot " + std::to_string(hinfo) + " is not positive); increase the diagonal shift");

@@ -14,7 +14,7 @@ namespace angpu {
 
 // x = A^{-1} b, A Hermitian positive definite P x P row-major (upper triangle read, overwritten by its Cholesky factor), b overwritten
 // by x; info_dev[0] = 0 or the 1-based index of the first non-positive pivot (cholesky.cu)
-void cholesky_solve(cplx* A, cplx* b, unsigned P, int* info_dev);
+void cholesky_solve(cplx* A, cplx* b, unsigned P, int* info_dev, DevBuf<cplx>& work);
 
 struct Ensemble {
     bool is_mc = false;

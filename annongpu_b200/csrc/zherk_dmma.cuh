@@ -53,6 +53,20 @@ __global__ void __launch_bounds__(128 * NWN) k_zherk_dmma(const double* __restri
         for(int b = 0; b < NB; b++) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
     unsigned buf = 0;
     if(s0 < s1) issue(s0, 0);
+    if(SUB) {
+        // C - G: the accumulators of the even-row lanes start at -C (their 2 x 2 real block folds to the complex entry below), so the
+        // read of C overlaps the first operand stage and the epilogue is store-only
+        #pragma unroll
+        for(int a = 0; a < 4; a++)
+            #pragma unroll
+            for(int b = 0; b < NB; b++) {
+                const unsigned k = tr * 64u + (m0 + 8u * a + row) / 2u, kp = tc * 64u + (n0 + 8u * b) / 2u + kq;
+                if((row & 1u) == 0u && k < P && kp < P && (!diag || kp >= k)) {
+                    const cplx c = Sout[(size_t)k * ldc + kp];
+                    acc[a][b][0] = -c.re; acc[a][b][1] = -c.im;
+                }
+            }
+    }
     for(size_t sb = s0; sb < s1; sb += ZD_KT, buf ^= 1u) {
         if(sb + ZD_KT < s1) { issue(sb + ZD_KT, buf ^ 1u); cp_async_wait<1>(); } else cp_async_wait<0>();
         __syncthreads();
@@ -91,10 +105,7 @@ __global__ void __launch_bounds__(128 * NWN) k_zherk_dmma(const double* __restri
                     cplx v(acc[a][b][0] + p1, acc[a][b][1] - p0);
                     if(k == kp) v.im = 0.0;
                     if(SUB) {
-                        cplx c = Sp[(size_t)k * ldc + kp];
-                        c -= v;
-                        if(k == kp) c.im = 0.0;
-                        Sp[(size_t)k * ldc + kp] = c;
+                        Sp[(size_t)k * ldc + kp] = cplx(-v.re, -v.im);          // v = G - C
                     } else {
                         Sp[(size_t)k * ldc + kp] = v;
                         if(k != kp) Sp[(size_t)kp * ldc + k] = conj(v);
