@@ -53,6 +53,7 @@ void port_activation(double re, double im, unsigned layer, double* lc_out, doubl
 
 /* ------------------------------------------------------------------ spins
  * include/basis/Spins.h:104-108 (operator[]: bit set <=> +1), :291-296 (enumerate: index == mask). */
+static inline unsigned words_for_c(unsigned n) { return (n + 63u) / 64u; }
 static inline double spin_at(const uint64_t* conf, unsigned i) {
     return (conf[i >> 6] >> (i & 63u)) & 1u ? 1.0 : -1.0;
 }
@@ -112,6 +113,58 @@ static cx op_fast_local_energy(const op_t* op, const uint64_t* conf) {
     return r;
 }
 
+/* ------------------------------------------------------------------ Pauli-string basis (density-matrix ensembles)
+ * A configuration is a Pauli string x = (a, b) over num_sites sites (I=(0,0) X=(1,0) Y=(0,1) Z=(1,1)).  The network sees it
+ * through 3 num_sites input units, unit 3 s + t = +1 iff x[s] - 1 == t, else -1 (PauliString::network_unit_at,
+ * include/basis/PauliString.hpp:84-90; PsiDeep::update_angles, PsiDeep.hpp:283-307).  Stored form here and on the GPU: the
+ * "units" bit mask (bit 3 s + t set iff the unit is +1), on which the spin-basis network code applies unchanged. */
+void port_paulis_to_units(const uint64_t* a, const uint64_t* b, unsigned num_sites, uint64_t* units) {
+    for(unsigned w = 0; w < words_for_c(3u * num_sites); w++) units[w] = 0;
+    for(unsigned s = 0; s < num_sites; s++) {
+        const unsigned t = (unsigned)((a[s >> 6] >> (s & 63u)) & 1u) | ((unsigned)((b[s >> 6] >> (s & 63u)) & 1u) << 1);
+        if(t) { const unsigned u = 3u * s + t - 1u; units[u >> 6] |= 1ull << (u & 63u); }
+    }
+}
+void port_units_to_paulis(const uint64_t* units, unsigned num_sites, uint64_t* a, uint64_t* b) {
+    for(unsigned w = 0; w < words_for_c(num_sites); w++) a[w] = b[w] = 0;
+    for(unsigned s = 0; s < num_sites; s++) {
+        unsigned t = 0;
+        for(unsigned k = 0; k < 3u; k++) { const unsigned u = 3u * s + k; if((units[u >> 6] >> (u & 63u)) & 1u) t = k + 1u; }
+        if(t & 1u) a[s >> 6] |= 1ull << (s & 63u);
+        if(t & 2u) b[s >> 6] |= 1ull << (s & 63u);
+    }
+}
+/* PauliString::apply(PauliString), include/basis/PauliString.hpp:257-277: P x = factor * (P xor x) */
+static inline cx pauli_mul(const uint64_t* Pa, const uint64_t* Pb, const uint64_t* xa, const uint64_t* xb, unsigned words,
+                           uint64_t* oa, uint64_t* ob) {
+    unsigned nneg = 0, neps = 0;
+    for(unsigned w = 0; w < words; w++) {
+        const uint64_t px = Pa[w] & ~Pb[w], py = ~Pa[w] & Pb[w], pz = Pa[w] & Pb[w];
+        const uint64_t xx = xa[w] & ~xb[w], xy = ~xa[w] & xb[w], xz = xa[w] & xb[w];
+        nneg += (unsigned)__builtin_popcountll((px & xz) | (py & xx) | (pz & xy));
+        neps += (unsigned)__builtin_popcountll((Pa[w] | Pb[w]) & (xa[w] | xb[w]) & ((Pa[w] ^ xa[w]) | (Pb[w] ^ xb[w])));
+        oa[w] = Pa[w] ^ xa[w]; ob[w] = Pb[w] ^ xb[w];
+    }
+    cx f = 1.0;
+    if(nneg & 1u) f *= -1.0;
+    if((neps & 3u) > 1u) f *= -1.0;
+    if(neps & 1u) f *= -1.0 * I;
+    return f;
+}
+void port_pauli_mul(const uint64_t* Pa, const uint64_t* Pb, const uint64_t* xa, const uint64_t* xb, unsigned words,
+                    double* coeff_out, uint64_t* a_out, uint64_t* b_out) {
+    const cx f = pauli_mul(Pa, Pb, xa, xb, words, a_out, b_out);
+    coeff_out[0] = creal(f); coeff_out[1] = cimag(f);
+}
+/* PauliString::enumerate, :33-38: site s takes type (index >> 2 s) & 3 */
+void port_paulis_enumerate(uint64_t index, unsigned num_sites, uint64_t* a, uint64_t* b) {
+    for(unsigned w = 0; w < words_for_c(num_sites); w++) a[w] = b[w] = 0;
+    for(unsigned s = 0; s < num_sites && s < 32u; s++) {
+        if((index >> (2u * s)) & 1u) a[s >> 6] |= 1ull << (s & 63u);
+        if((index >> (2u * s + 1u)) & 1u) b[s >> 6] |= 1ull << (s & 63u);
+    }
+}
+
 /* ------------------------------------------------------------------ wavefunctions */
 enum { K_RBM = 0, K_DEEP = 1, K_CNN = 2, K_CLASSICAL = 3 };
 
@@ -130,6 +183,7 @@ typedef struct {
 typedef struct psi_s {
     int       kind;
     unsigned  N, words, num_params;
+    unsigned  num_sites;   /* physical sites; N == 3 num_sites marks a PsiDeep on the Pauli-string basis (one input unit per site and Pauli type) */
     cx        log_prefactor;
     /* RBM  (include/quantum_state/PsiRBM.hpp:42-67) */
     unsigned  M; cx* W; cx final_weight;
@@ -180,7 +234,7 @@ psi_t* port_deep_create(unsigned num_sites, unsigned N, const double* input_weig
                         const unsigned* lhs_connections, const double* lhs_weights,
                         const double* final_weights, const double* lp) {
     psi_t* p = (psi_t*)calloc(1, sizeof(psi_t));
-    p->kind = K_DEEP; p->N = N; p->words = words_for(num_sites); p->num_layers = num_hidden + 1;
+    p->kind = K_DEEP; p->N = N; p->num_sites = num_sites; p->words = words_for(N); p->num_layers = num_hidden + 1;
     p->log_prefactor = lp[0] + lp[1] * I;
     p->input_weights = (cx*)malloc(sizeof(cx) * N);
     for(unsigned i = 0; i < N; i++) p->input_weights[i] = input_weights[2 * i] + input_weights[2 * i + 1] * I;
@@ -540,6 +594,29 @@ static cx op_local_energy(const op_t* op, const psi_t* p, payload_t* pl, const u
     return result;
 }
 
+/* The same on the Pauli-string basis: `units` is the network-side mask of the Pauli string x; a string P of the operator maps it
+ * to factor * (P xor x) (pauli_mul); only the identity string is diagonal (PauliString::is_diagonal_on_basis(PauliString), :163-165). */
+static cx op_local_energy_paulis(const op_t* op, const psi_t* p, payload_t* pl, const uint64_t* units, cx log_psi) {
+    cx result = 0.0;
+    uint64_t xa[MAXW], xb[MAXW], na[MAXW], nb[MAXW], prime[MAXW];
+    port_units_to_paulis(units, p->num_sites, xa, xb);
+    for(unsigned n = 0; n < op->n; n++) {
+        const cx me = pauli_mul(op->a + n * op->words, op->b + n * op->words, xa, xb, op->words, na, nb) * op->coef[n];
+        port_paulis_to_units(na, nb, p->num_sites, prime);
+        if(!conf_equal(units, prime, p->words)) {
+            payload_update(p, pl, units, prime);
+            const cx lp = psi_log_psi(p, pl, prime);
+            result += me * cexp(lp - log_psi);
+            payload_update(p, pl, prime, units);
+        } else result += me;
+    }
+    return result;
+}
+static inline int psi_on_paulis(const psi_t* p) { return p->kind == K_DEEP && p->num_sites && p->N == 3u * p->num_sites; }
+static inline cx local_energy_any(const op_t* op, const psi_t* p, payload_t* pl, const uint64_t* conf, cx log_psi) {
+    return psi_on_paulis(p) ? op_local_energy_paulis(op, p, pl, conf, log_psi) : op_local_energy(op, p, pl, conf, log_psi);
+}
+
 /* ------------------------------------------------------------------ single-configuration probes
  * source/network_functions/PsiVector.cu.template:102-133, PsiOkVector.cu.template:41-74. */
 void port_log_psi_s(const psi_t* p, const uint64_t* conf, double* out) {
@@ -556,7 +633,7 @@ void port_psi_O_k(const psi_t* p, const uint64_t* conf, double* out) {
 void port_local_energy(const psi_t* p, const op_t* op, const uint64_t* conf, double* out) {
     payload_t* pl = payload_new(p); payload_init(p, pl, conf);
     const cx lp = psi_log_psi(p, pl, conf);
-    const cx e = op_local_energy(op, p, pl, conf, lp); out[0] = creal(e); out[1] = cimag(e);
+    const cx e = local_energy_any(op, p, pl, conf, lp); out[0] = creal(e); out[1] = cimag(e);
     payload_free(pl);
 }
 
@@ -580,7 +657,7 @@ void port_eval_samples(const psi_t* p, const op_t* op, const uint64_t* confs, un
             const cx lp = psi_log_psi(p, pl, conf);
             if(log_psi_out) { log_psi_out[2 * s] = creal(lp); log_psi_out[2 * s + 1] = cimag(lp); }
             if(eloc_out && op) {
-                const cx e = op_local_energy(op, p, pl, conf, lp);
+                const cx e = local_energy_any(op, p, pl, conf, lp);
                 eloc_out[2 * s] = creal(e); eloc_out[2 * s + 1] = cimag(e);
             }
             if(O_out) {
@@ -632,11 +709,26 @@ static void mc_chain(const psi_t* p, const mc_params_t* mc, unsigned long chain,
     const uint32_t k0 = (uint32_t)mc->seed, k1 = (uint32_t)(mc->seed >> 32);
     const uint32_t gchain = (uint32_t)(mc->chain0 + chain);
     uint32_t r[4];
+    const int paulis = psi_on_paulis(p);
+    if(paulis) {
+        /* Init_Policy<PauliString> = PauliString::set_randomly (policies/Init_Policy.hpp:32-42, PauliString.hpp:59-65): two random
+         * masks, both cut with (1 << (num_sites % 64)) - 1 -- which is 0 for num_sites = 64 (kept) */
+        uint64_t a[MAXW] = {0}, b[MAXW] = {0};
+        const unsigned sw = words_for_c(p->num_sites);
+        for(unsigned w = 0; w < sw; w++) {
+            philox4x32_10(w, 0u, gchain, (mc->call << 1) | 0u, k0, k1, r);
+            a[w] = (uint64_t)r[0] | ((uint64_t)r[1] << 32); b[w] = (uint64_t)r[2] | ((uint64_t)r[3] << 32);
+        }
+        const uint64_t cut = (1ull << (p->num_sites % 64u)) - 1ull;
+        a[sw - 1] &= cut; b[sw - 1] &= cut;
+        port_paulis_to_units(a, b, p->num_sites, conf);
+    } else {
     for(unsigned w = 0; w < p->words; w++) {
         philox4x32_10(w, 0u, gchain, (mc->call << 1) | 0u, k0, k1, r);
         conf[w] = (uint64_t)r[0] | ((uint64_t)r[1] << 32);
     }
     if(p->N % 64u) conf[p->words - 1] &= (1ull << (p->N % 64u)) - 1ull;
+    }
     payload_init(p, pl, conf);
     cx log_psi = psi_log_psi(p, pl, conf);
     uint64_t t = 0;
@@ -646,9 +738,16 @@ static void mc_chain(const psi_t* p, const mc_params_t* mc, unsigned long chain,
         const unsigned long nsteps = (s == 0) ? therm : per_sample;
         for(unsigned long i = 0; i < nsteps; i++, t++) {
             philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), gchain, (mc->call << 1) | 1u, k0, k1, r);
-            const unsigned site = r[0] % p->N;
             memcpy(next, conf, sizeof(conf));
-            next[site >> 6] ^= 1ull << (site & 63u);
+            if(paulis) {
+                /* Update_Policy<PauliString> (policies/Update_Policy.hpp:38-55): one random number x, site x % num_sites takes type x >> 30 */
+                const unsigned site = r[0] % p->num_sites, type = r[0] >> 30;
+                for(unsigned k = 0; k < 3u; k++) { const unsigned u = 3u * site + k; next[u >> 6] &= ~(1ull << (u & 63u)); }
+                if(type) { const unsigned u = 3u * site + type - 1u; next[u >> 6] |= 1ull << (u & 63u); }
+            } else {
+                const unsigned site = r[0] % p->N;
+                next[site >> 6] ^= 1ull << (site & 63u);
+            }
             payload_update(p, pl, conf, next);
             const cx nlp = psi_log_psi(p, pl, next);
             const double ratio = exp(2.0 * (creal(nlp) - creal(log_psi)));
@@ -710,7 +809,7 @@ void port_mc_gradient(const psi_t* p, const op_t* op, unsigned long num_samples,
             const uint64_t* conf = confs + s * p->words;
             payload_init(p, pl, conf);
             const cx lp = psi_log_psi(p, pl, conf);
-            const cx e = op_local_energy(op, p, pl, conf, lp);
+            const cx e = local_energy_any(op, p, pl, conf, lp);
             e_loc_sum += weight * e;
             memset(row, 0, sizeof(cx) * P);
             payload_init(p, pl, conf);

@@ -65,6 +65,10 @@ def lib():
         L.port_philox.argtypes = [vp, vp, vp]
         L.port_mc_sample.argtypes = [vp, ul, u32, u32, ul, u64, C.c_uint32, ul, vp, vp, vp, i32]
         L.port_mc_gradient.argtypes = [vp, vp, ul, u32, u32, ul, u64, C.c_uint32, vp, vp, vp, i32]
+        L.port_paulis_to_units.argtypes = [vp, vp, u32, vp]
+        L.port_units_to_paulis.argtypes = [vp, u32, vp, vp]
+        L.port_pauli_mul.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp]
+        L.port_paulis_enumerate.argtypes = [u64, u32, vp, vp]
         _lib = L
     return _lib
 
@@ -293,8 +297,53 @@ class ExactSummation:
         return confs, None  # weights derive from log psi
 
 
+# ---- Pauli-string basis (density-matrix ensembles).  A PsiDeep with N == 3 num_sites input units lives on
+# this basis; configurations are handed around as the network-side "units" mask (vmc_port.c: port_paulis_to_units).
+
+def paulis_to_units(a, b, num_sites):
+    a, b = _u64(a).reshape(-1), _u64(b).reshape(-1)
+    out = np.zeros(words_for(3 * num_sites), np.uint64)
+    lib().port_paulis_to_units(_p(a), _p(b), num_sites, _p(out))
+    return out
+
+
+def units_to_paulis(units, num_sites):
+    units = _u64(units).reshape(-1)
+    a, b = np.zeros(words_for(num_sites), np.uint64), np.zeros(words_for(num_sites), np.uint64)
+    lib().port_units_to_paulis(_p(units), num_sites, _p(a), _p(b))
+    return a, b
+
+
+def pauli_mul(Pa, Pb, xa, xb, words=1):
+    """PauliString::apply(PauliString) (include/basis/PauliString.hpp:257-277): (factor, a', b')."""
+    Pa, Pb, xa, xb = (conf_words(v, words) if np.isscalar(v) else _u64(v) for v in (Pa, Pb, xa, xb))
+    c, oa, ob = np.empty(1, np.complex128), np.zeros(words, np.uint64), np.zeros(words, np.uint64)
+    lib().port_pauli_mul(_p(Pa), _p(Pb), _p(xa), _p(xb), words, _p(c), _p(oa), _p(ob))
+    return complex(c[0]), oa, ob
+
+
+def paulis_enumerate(index, num_sites):
+    a, b = np.zeros(words_for(num_sites), np.uint64), np.zeros(words_for(num_sites), np.uint64)
+    lib().port_paulis_enumerate(int(index), num_sites, _p(a), _p(b))
+    return a, b
+
+
+def enumerate_pauli_units(num_sites):
+    """All 4^num_sites Pauli strings in PauliString::enumerate order, as units masks (ns, words_for(3 num_sites))."""
+    return np.stack([paulis_to_units(*paulis_enumerate(i, num_sites), num_sites) for i in range(4 ** num_sites)])
+
+
+class ExactSummationPaulis:
+    """ExactSummation_t<PauliString> (include/ensembles/ExactSummation.hpp:124-126)."""
+
+    def __init__(self, num_sites):
+        self.num_sites = num_sites
+        self.num_steps = 4 ** num_sites
+
+
 class MonteCarlo:
-    """Philox-driven restatement of MonteCarlo_t (all chains run; see vmc_port.c header)."""
+    """Philox-driven restatement of MonteCarlo_t (all chains run; see vmc_port.c header).  With a PsiDeep on the Pauli-string
+    basis (N == 3 num_sites) the chain uses Init_Policy / Update_Policy<PauliString> -- MonteCarloPaulis is the same class."""
 
     def __init__(self, num_samples, num_sweeps, num_thermalization_sweeps, num_markov_chains, seed=0xA11CE, chain0=0):
         self.num_samples, self.num_sweeps = num_samples, num_sweeps
@@ -319,7 +368,15 @@ class MonteCarlo:
         return self.acceptances / max(1, self.acceptances + self.rejections)
 
 
+MonteCarloPaulis = MonteCarlo
+
+
 def _samples_and_weights(psi, ens):
+    if isinstance(ens, ExactSummationPaulis):
+        assert psi.N == 3 * ens.num_sites
+        confs = enumerate_pauli_units(ens.num_sites)
+        lp, _, _ = eval_samples(psi, None, confs)
+        return confs, lp, np.exp(2.0 * lp.real)
     if isinstance(ens, ExactSummation):
         confs = enumerate_confs(ens.num_sites)
         lp, _, _ = eval_samples(psi, None, confs)

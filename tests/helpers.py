@@ -175,3 +175,15 @@ class GpuAdapter:
 
     def psi_O_k(self, psi, conf):
         return self.A.psi_O_k(psi, np.asarray(conf, dtype=np.uint64))
+
+
+def pauli_zoo():
+    """Pauli-string-basis (density-matrix) cases, SURVEY.md §8f rank 3: name -> (DeepSpec with N = 3 num_sites, PauliSum, num_sites).
+    The operator has complex coefficients and every Pauli type, so that all branches of PauliString::apply(PauliString) are hit."""
+    z = {}
+    for name, ns, M, C, seed in (("pdeep3", 3, [9, 3], [3, 3], 31), ("pdeep4", 4, [12], [6], 32), ("pdeep2x2h", 2, [6, 6], [6, 3], 33)):
+        spec = F.deep_spec(ns, 3 * ns, M, C, noise=0.3, final_weights=0.7, seed=seed)
+        H = F.heisenberg(ns, F.ring_bonds(ns)) if ns > 2 else F.heisenberg(ns, [(0, 1)])
+        H = H + (0.3 - 0.2j) * F.sigma_x(0, ns) + (0.1 + 0.4j) * F.sigma_y(ns - 1, ns) * F.sigma_z(0, ns) + 0.25 * F.sigma_z(1, ns) + 0.5
+        z[name] = (spec, H, ns)
+    return z
