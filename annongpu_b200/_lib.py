@@ -57,6 +57,8 @@ _SIGNATURES = {
     "angpu_psi_set_log_prefactor": [vp, vp],
     "angpu_es_create": [u32, vp],
     "angpu_mc_create": [ull, u32, u32, u32, u64, vp],
+    "angpu_es_paulis_create": [u32, vp],
+    "angpu_mc_paulis_create": [ull, u32, u32, u32, u64, vp],
     "angpu_ensemble_copy": [vp, vp],
     "angpu_ensemble_destroy": [vp],
     "angpu_ensemble_num_steps": [vp, vp],

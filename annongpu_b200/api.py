@@ -26,7 +26,8 @@ from .factories import PauliSum, masks_to_words, words_for
 
 __all__ = [
     "PsiRBM", "PsiDeep", "PsiCNN", "PsiClassicalFP_1", "PsiClassicalFP_2", "PsiClassicalANN_1", "PsiClassicalANN_2",
-    "PsiFullyPolarized", "Operator", "Spins", "MonteCarloSpins", "ExactSummationSpins", "ExpectationValue", "TDVP",
+    "PsiFullyPolarized", "Operator", "Spins", "MonteCarloSpins", "ExactSummationSpins", "MonteCarloPaulis", "ExactSummationPaulis",
+    "paulis_to_units", "units_to_paulis", "ExpectationValue", "TDVP",
     "HilbertSpaceDistance", "KullbackLeibler",
     "log_psi_s", "psi_O_k", "psi_O_k_vector", "log_psi", "psi_vector", "log_psi_vector", "apply_operator",
     "local_energies", "activation_function", "pauli_apply", "setDevice", "start_profiling", "stop_profiling",
@@ -249,8 +250,16 @@ class _Psi:
         return self.copy()
 
     @property
+    def pauli_sites(self):
+        """!= 0: a network on the Pauli-string basis (PsiDeep with N = 3 num_sites input units), to be used with MonteCarloPaulis /
+        ExactSummationPaulis; its configurations are units masks (paulis_to_units)."""
+        n, N = getattr(self, "num_sites", 0), getattr(self, "N", 0)
+        return n if (isinstance(self, PsiDeep) and n and N == 3 * n) else 0
+
+    @property
     def words(self):
-        return words_for(self.num_sites)
+        """uint64 words of one configuration as it crosses the boundary."""
+        return words_for(3 * self.num_sites) if self.pauli_sites else words_for(self.num_sites)
 
     @property
     def num_params(self):
@@ -618,6 +627,17 @@ class ExactSummationSpins(_Ensemble):
         call("angpu_es_create", self.num_sites, C.byref(self._h))
 
 
+class ExactSummationPaulis(_Ensemble):
+    """ExactSummationPaulis(num_sites, gpu) (pyANNonGPU/main.cpp.template:400-405): all 4^num_sites Pauli strings, for a PsiDeep with
+    N = 3 num_sites input units (the density-matrix basis)."""
+
+    def __init__(self, num_sites, gpu=True):
+        _require_gpu(gpu)
+        self.num_sites = int(num_sites)
+        self._h = C.c_void_p()
+        call("angpu_es_paulis_create", self.num_sites, C.byref(self._h))
+
+
 class MonteCarloSpins(_Ensemble):
     """MonteCarloSpins(num_samples, num_sweeps, num_thermalization_sweeps, num_markov_chains, gpu)
     (pyANNonGPU/main.cpp.template:358-366) + seed; or MonteCarloSpins(other) (copy)."""
@@ -626,6 +646,7 @@ class MonteCarloSpins(_Ensemble):
         self._h = C.c_void_p()
         if isinstance(num_samples, MonteCarloSpins):
             other = num_samples
+            assert type(other) is type(self), "copy between MonteCarloSpins and MonteCarloPaulis"
             self.__dict__.update({k: v for k, v in other.__dict__.items() if k != "_h"})
             call("angpu_ensemble_copy", other._h, C.byref(self._h))
             return
@@ -633,8 +654,10 @@ class MonteCarloSpins(_Ensemble):
         self.num_samples, self.num_sweeps = int(num_samples), int(num_sweeps)
         self.num_thermalization_sweeps, self.num_markov_chains = int(num_thermalization_sweeps), int(num_markov_chains)
         self.seed = int(seed)
-        call("angpu_mc_create", self.num_samples, self.num_sweeps, self.num_thermalization_sweeps, self.num_markov_chains,
+        call(self._create, self.num_samples, self.num_sweeps, self.num_thermalization_sweeps, self.num_markov_chains,
              self.seed, C.byref(self._h))
+
+    _create = "angpu_mc_create"
 
     @property
     def acceptances(self):
@@ -670,7 +693,40 @@ class MonteCarloSpins(_Ensemble):
 # -------------------------------------------------------------------------------------------- functionals
 
 def _match(op, psi):
-    return op.with_words(psi.words) if op.words != psi.words else op
+    w = words_for(psi.num_sites) if psi.pauli_sites else psi.words          # operator masks are SITE masks on either basis
+    return op.with_words(w) if op.words != w else op
+
+
+class MonteCarloPaulis(MonteCarloSpins):
+    """MonteCarloPaulis(num_samples, num_sweeps, num_thermalization_sweeps, num_markov_chains, gpu) (pyANNonGPU/main.cpp.template:369-377):
+    Markov chains over Pauli strings (Init_Policy / Update_Policy<PauliString>), for a PsiDeep with N = 3 num_sites input units.
+    A sweep is 3 num_sites proposals (MonteCarlo.hpp:90-101 counts psi.get_num_input_units())."""
+    _create = "angpu_mc_paulis_create"
+
+
+def paulis_to_units(a, b, num_sites):
+    """The boundary form of a Pauli string (a, b): bit 3 s + t set iff site s carries type t + 1 (PauliString::network_unit_at)."""
+    a, b = int(a), int(b)
+    words = (3 * num_sites + 63) // 64
+    v = 0
+    for s in range(num_sites):
+        t = ((a >> s) & 1) | (((b >> s) & 1) << 1)
+        if t:
+            v |= 1 << (3 * s + t - 1)
+    return np.array([(v >> (64 * w)) & 0xFFFFFFFFFFFFFFFF for w in range(words)], dtype=np.uint64)
+
+
+def units_to_paulis(units, num_sites):
+    v = sum(int(x) << (64 * w) for w, x in enumerate(np.asarray(units, dtype=np.uint64).ravel()))
+    a = b = 0
+    for s in range(num_sites):
+        t = 0
+        for k in range(3):
+            if (v >> (3 * s + k)) & 1:
+                t = k + 1
+        a |= (t & 1) << s
+        b |= (t >> 1) << s
+    return a, b
 
 
 class ExpectationValue:

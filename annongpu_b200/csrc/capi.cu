@@ -167,10 +167,26 @@ int angpu_mc_create(unsigned long long num_samples, unsigned num_sweeps, unsigne
     *out = e;
     API_END
 }
+// MonteCarloPaulis / ExactSummationPaulis (pyANNonGPU/main.cpp.template:369-377, 400-405): configurations are Pauli strings
+int angpu_es_paulis_create(unsigned num_sites, angpu_ensemble_t* out) {
+    API_BEGIN NOTNULL(out);
+    ANGPU_REQUIRE(num_sites >= 1 && num_sites <= 20u, "ExactSummationPaulis: 1 <= num_sites <= 20");
+    auto* e = new angpu_ensemble_s(); e->e.is_mc = false; e->e.paulis = true; e->e.num_sites = num_sites; *out = e;
+    API_END
+}
+int angpu_mc_paulis_create(unsigned long long num_samples, unsigned num_sweeps, unsigned num_therm, unsigned num_chains, uint64_t seed, angpu_ensemble_t* out) {
+    API_BEGIN NOTNULL(out);
+    ANGPU_REQUIRE(num_chains >= 1, "MonteCarlo: num_markov_chains must be >= 1");
+    ANGPU_REQUIRE(num_samples >= 1, "MonteCarlo: num_samples must be >= 1");
+    auto* e = new angpu_ensemble_s(); e->e.is_mc = true; e->e.paulis = true;
+    e->e.num_samples = num_samples; e->e.num_sweeps = num_sweeps; e->e.num_therm = num_therm; e->e.num_chains = num_chains; e->e.seed = seed;
+    *out = e;
+    API_END
+}
 int angpu_ensemble_copy(angpu_ensemble_t ens, angpu_ensemble_t* out) {
     API_BEGIN NOTNULL(ens); NOTNULL(out);
     auto* e = new angpu_ensemble_s(); const Ensemble& s = ens->e;
-    e->e.is_mc = s.is_mc; e->e.num_sites = s.num_sites; e->e.num_samples = s.num_samples; e->e.num_sweeps = s.num_sweeps;
+    e->e.is_mc = s.is_mc; e->e.paulis = s.paulis; e->e.num_sites = s.num_sites; e->e.num_samples = s.num_samples; e->e.num_sweeps = s.num_sweeps;
     e->e.num_therm = s.num_therm; e->e.num_chains = s.num_chains; e->e.call = s.call; e->e.seed = s.seed; e->e.rank = s.rank; e->e.world = s.world;
     *out = e;
     API_END

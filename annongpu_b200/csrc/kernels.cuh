@@ -20,6 +20,7 @@ struct McParams {
     unsigned           num_chains_local;   // chains run by this process
     unsigned           chain0;             // global id of the first local chain
     unsigned           seed_lo, seed_hi, call;
+    unsigned           pauli_sites;        // 0: spin basis; else the chains run over Pauli strings of that many sites (pauli_basis.cuh)
 };
 
 // per-warp shared-memory slice: [payload cplx x pl_elems][conf u64 x MAXW][conf' u64 x MAXW]

@@ -36,6 +36,9 @@ struct Operator {
     unsigned num_sites_touched = 0;        // 1 + the highest site any string acts on (0 for a pure identity)
     DevBuf<cplx> d_coef; DevBuf<uint64_t> d_b, d_flip; DevBuf<unsigned> d_group_begin;
     OpDev dev{};
+    // the strings as given (caller's order, nothing folded in): the layout of the Pauli-string basis, where a string acts by Pauli
+    // multiplication (pauli_basis.cuh)
+    DevBuf<cplx> d_pcoef; DevBuf<uint64_t> d_pa, d_pb;
 
     Operator(unsigned n, const double* coeffs, const uint64_t* a, const uint64_t* b, unsigned words_) : num_strings(n), words(words_) {
         ANGPU_REQUIRE(words >= 1 && words <= (unsigned)MAXW, "operator: words must be in 1..4");
@@ -85,6 +88,7 @@ struct Operator {
                 if(m) num_sites_touched = std::max(num_sites_touched, w * 64u + 64u - (unsigned)__builtin_clzll(m));
             }
         d_coef.upload(coef); d_b.upload(bmask); d_flip.upload(flip); d_group_begin.upload(begin);
+        d_pcoef.upload(h_coef); d_pa.upload(h_a); d_pb.upload(h_b);
         dev = OpDev{num_strings, num_diag, ng, words, max_flips, d_coef.p, d_b.p, d_flip.p, d_group_begin.p};
     }
 };

@@ -6,6 +6,7 @@
 #include "rbm_sampler.cuh"
 #include "deep_kernels.cuh"
 #include "cnn_kernels.cuh"
+#include "pauli_basis.cuh"
 #include <algorithm>
 #include <set>
 #include <string>
@@ -364,8 +365,11 @@ void PsiRBM::mc_sample(const McParams& mc, SampleSet& S, unsigned long long* acc
 PsiDeep::PsiDeep(unsigned num_sites_, unsigned N_, const cplx* input_weights_, unsigned num_hidden, const unsigned* sizes,
                  const unsigned* conn, const cplx* biases, const unsigned* lhs_connections, const cplx* lhs_weights,
                  const cplx* final_weights_, cplx lp_) {
-    kind = DEEP; num_sites = num_sites_; N = N_; words = words_for(num_sites_); lp = lp_;
-    ANGPU_REQUIRE(N == num_sites, "PsiDeep: only the spin basis (N == num_sites) is on the hot path");
+    kind = DEEP; num_sites = num_sites_; N = N_; words = words_for(N_); lp = lp_;
+    // N == num_sites: spin basis.  N == 3 num_sites: the Pauli-string basis, one input unit per site and Pauli type
+    // (PsiDeep.hpp:282-308, PauliString::network_unit_at) -- to be used with MonteCarloPaulis / ExactSummationPaulis.
+    ANGPU_REQUIRE(N == num_sites || N == 3u * num_sites, "PsiDeep: N must be num_sites (spin basis) or 3 num_sites (Pauli-string basis)");
+    pauli_sites = (N == 3u * num_sites && num_sites > 0u) ? num_sites : 0u;
     ANGPU_REQUIRE(N >= 1 && N <= 64u * MAXW, "PsiDeep: 1 <= N <= 256");
     ANGPU_REQUIRE(num_hidden >= 1 && num_hidden + 1 <= (unsigned)DEEP_MAX_LAYERS, "PsiDeep: 1..4 hidden layers");
     num_layers = num_hidden + 1;
@@ -393,7 +397,7 @@ PsiDeep::PsiDeep(unsigned num_sites_, unsigned N_, const cplx* input_weights_, u
     upload();
 }
 PsiDeep::PsiDeep(const PsiDeep& o) {
-    kind = DEEP; N = o.N; words = o.words; P = o.P; lp = o.lp;
+    kind = DEEP; N = o.N; words = o.words; P = o.P; lp = o.lp; pauli_sites = o.pauli_sites;
     num_sites = o.num_sites; num_layers = o.num_layers; width = o.width; num_deep = o.num_deep;
     input_weights = o.input_weights; final_weights = o.final_weights;
     layers.resize(num_layers);
@@ -484,6 +488,20 @@ void PsiDeep::set_params(const cplx* in) {
 }
 void PsiDeep::log_psi(SampleSet& S, bool es_weights) { generic_log_psi(dev(), S, es_weights); }
 void PsiDeep::eloc(const Operator& op, SampleSet& S) {
+    ANGPU_REQUIRE(S.pauli_sites == pauli_sites, pauli_sites ? "PsiDeep on the Pauli-string basis (N = 3 num_sites): use MonteCarloPaulis / ExactSummationPaulis"
+                                                            : "Pauli-string ensembles need a PsiDeep with N = 3 num_sites input units");
+    if(pauli_sites) {
+        ANGPU_REQUIRE(op.words == words_for(num_sites) && op.words <= (unsigned)PAULI_SITE_WORDS, "operator / wavefunction word count mismatch");
+        ANGPU_REQUIRE(op.num_sites_touched <= num_sites, "operator acts on site " + std::to_string(op.num_sites_touched - 1) + " but the wavefunction has " + std::to_string(num_sites) + " sites");
+        if(S.ns == 0) return;
+        const DeepDev d = dev();
+        const WarpCfg c = warp_cfg(d.payload_elems(), S.ns, d.block_scratch_bytes());
+        set_smem(k_eloc_paulis<DeepDev>, c.smem);
+        const PauliOpDev pop{op.num_strings, op.words, op.d_pcoef.p, op.d_pa.p, op.d_pb.p};
+        k_eloc_paulis<DeepDev><<<c.grid, c.wpb * 32, c.smem, stream()>>>(d, pop, num_sites, S.conf.p, S.log_psi.p, S.ns, S.eloc.p);
+        ANGPU_CHECK_LAUNCH(); count_launch();
+        return;
+    }
     require_operator_fits(op, N, words);
     if(S.ns == 0) return;
     const char* env_s = getenv("ANGPU_DEEP_ELOC");              // "generic" forces the warp-per-sample kernel
@@ -496,6 +514,22 @@ void PsiDeep::eloc(const Operator& op, SampleSet& S) {
 }
 void PsiDeep::ok_rows(SampleSet& S, size_t s0, size_t cnt, cplx* out) { generic_ok(dev(), S, s0, cnt, out); }
 void PsiDeep::mc_sample(const McParams& mc, SampleSet& S, unsigned long long* a) {
+    ANGPU_REQUIRE(mc.pauli_sites == pauli_sites, pauli_sites ? "PsiDeep on the Pauli-string basis (N = 3 num_sites): use MonteCarloPaulis"
+                                                             : "MonteCarloPaulis needs a PsiDeep with N = 3 num_sites input units");
+    if(pauli_sites) {
+        if(mc.num_chains_local == 0) return;
+        const DeepDev d = dev();
+        const size_t slice = warp_slice_bytes(d.payload_elems());
+        const size_t budget = std::min<size_t>(ctx().smem_optin, 200 * 1024);
+        ANGPU_REQUIRE(slice <= budget, "model scratch does not fit in shared memory");
+        unsigned wpb = (unsigned)std::min<size_t>(4, budget / slice);
+        while(wpb > 1 && wpb * slice > budget / 2) wpb--;
+        set_smem(k_mc_paulis<DeepDev>, wpb * slice);
+        k_mc_paulis<DeepDev><<<ceil_div(mc.num_chains_local, wpb), wpb * 32, wpb * slice, stream()>>>(d, mc, S.conf.p, S.log_psi.p, a);
+        ANGPU_CHECK_LAUNCH(); count_launch();
+        S.has_angles = false;
+        return;
+    }
     const char* env_s = getenv("ANGPU_DEEP_SAMPLER");          // "generic" forces the warp-per-chain kernel (tests, A/B timing)
     const bool force_generic = env_s && std::string(env_s) == "generic";
     if(!block_sampler_ok || force_generic) { generic_mc(dev(), mc, S, a); return; }

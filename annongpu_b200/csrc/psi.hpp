@@ -21,6 +21,7 @@ struct SampleSet {
     DevBuf<cplx>     eloc;      // [ns]
     DevBuf<cplx>     angles;    // [ns][A]  cached first-layer angles (PsiRBM fast path), valid iff has_angles
     bool     has_angles = false;
+    unsigned pauli_sites = 0;   // != 0: the configurations are Pauli strings of that many sites, stored as units masks (pauli_basis.cuh)
     void resize(size_t ns_, unsigned words_) {
         ns = ns_; words = words_;
         conf.resize(ns * words); log_psi.resize(ns); weight.resize(ns); eloc.resize(ns);
@@ -35,12 +36,13 @@ struct Psi {
     enum Kind { RBM = 0, DEEP = 1, CNN = 2, CLASSICAL = 3 };
     Kind     kind;
     unsigned N = 0, words = 1, P = 0;
+    unsigned pauli_sites = 0;   // != 0: a network on the Pauli-string basis (PsiDeep with N = 3 num_sites input units)
     cplx     lp{0.0, 0.0};
 
     // live-object registry: TDVP / HilbertSpaceDistance / KullbackLeibler keep a Psi* for the lazily materialised dense O rows;
     // a C-ABI caller may destroy the psi in between, which must surface as an error instead of a use-after-free
     Psi() { registry(this, +1); }
-    Psi(const Psi& o) : kind(o.kind), N(o.N), words(o.words), P(o.P), lp(o.lp) { registry(this, +1); }
+    Psi(const Psi& o) : kind(o.kind), N(o.N), words(o.words), P(o.P), pauli_sites(o.pauli_sites), lp(o.lp) { registry(this, +1); }
     virtual ~Psi() { registry(this, -1); }
     static bool is_live(const Psi* p) { return registry(p, 0); }
     virtual Psi* clone() const = 0;

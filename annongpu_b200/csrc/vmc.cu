@@ -1,5 +1,6 @@
 // Ensembles, reductions over samples, ExpectationValue / TDVP, S.v, CG and dense solve.
 #include "vmc.hpp"
+#include "pauli_basis.cuh"
 #include "dmma.cuh"
 #include "zherk_dmma.cuh"
 #include <string>
@@ -781,6 +782,10 @@ void Ensemble::generate(Psi& psi, SampleSet& S) {
     // collectives of this evaluation run iff the ensemble is sharded (an unsharded ensemble is never summed over ranks;
     // a sharded one without a transport reports this shard's partial sums -- rank emulation in one process, tests)
     set_reduce(world > 1);
+    // MonteCarloPaulis / ExactSummationPaulis (Pauli-string basis, pauli_basis.cuh): PsiDeep with N = 3 num_sites input units
+    ANGPU_REQUIRE(paulis ? psi.pauli_sites != 0u : psi.pauli_sites == 0u,
+                  paulis ? "Pauli-string ensembles need a PsiDeep with N = 3 num_sites input units" : "a PsiDeep on the Pauli-string basis needs MonteCarloPaulis / ExactSummationPaulis");
+    S.pauli_sites = psi.pauli_sites;
     if(is_mc) {
         ANGPU_REQUIRE(num_chains >= 1 && num_samples >= 1, "MonteCarlo: num_samples and num_markov_chains must be positive");
         size_t c0, cn; shard(num_chains, c0, cn);
@@ -788,12 +793,19 @@ void Ensemble::generate(Psi& psi, SampleSet& S) {
         mc.num_samples = num_samples; mc.num_sweeps = num_sweeps; mc.num_therm = num_therm;
         mc.steps_per_chain = (unsigned)(num_samples / num_chains);
         mc.num_chains_local = (unsigned)cn; mc.chain0 = (unsigned)c0;
-        mc.seed_lo = (unsigned)seed; mc.seed_hi = (unsigned)(seed >> 32); mc.call = call;
+        mc.seed_lo = (unsigned)seed; mc.seed_hi = (unsigned)(seed >> 32); mc.call = call; mc.pauli_sites = psi.pauli_sites;
         S.resize((size_t)mc.steps_per_chain * cn, psi.words);
         d_acc_rej.resize(4); d_acc_rej.zero();
         psi.mc_sample(mc, S, d_acc_rej.p);
         if(S.ns) { k_fill<<<grid_for(S.ns), 256, 0, stream()>>>(S.weight.p, 1.0 / (double)num_samples, S.ns); ANGPU_CHECK_LAUNCH(); count_launch(); }
         call++;
+    } else if(paulis) {
+        ANGPU_REQUIRE(num_sites == psi.pauli_sites, "ExactSummationPaulis: num_sites differs from the wavefunction's");
+        ANGPU_REQUIRE(num_sites <= 20u, "ExactSummationPaulis: too many sites (4^num_sites configurations)");
+        size_t b, n; shard((size_t)1 << (2u * num_sites), b, n);
+        S.resize(n, psi.words);
+        if(n) { k_enumerate_paulis<<<grid_for(n), 256, 0, stream()>>>(S.conf.p, b, n, num_sites, psi.words); ANGPU_CHECK_LAUNCH(); count_launch(); }
+        psi.log_psi(S, true);
     } else {
         ANGPU_REQUIRE(num_sites == psi.N, "ExactSummation: num_sites differs from the wavefunction's");
         ANGPU_REQUIRE(num_sites <= 40u, "ExactSummation: too many sites");
@@ -862,6 +874,7 @@ __global__ void k_exp_fast_energy(const OpDev op, const uint64_t* __restrict__ c
     }
 }
 cplx ExpectationValue::exp_sigma_z(const Operator& op, Psi& psi, Ensemble& ens) {
+    ANGPU_REQUIRE(!ens.paulis, "exp_sigma_z: spin-basis ensembles only (fast_local_energy of a diagonal operator on Spins)");
     require_operator_fits(op, psi.N, psi.words);
     ens.generate(psi, S);
     if(S.ns) {
@@ -1572,6 +1585,7 @@ void apply_operator(Psi& psi, const Operator& op, Ensemble& ens, cplx* out_host)
 }
 void local_energies(Psi& psi, const Operator& op, const uint64_t* confs_host, size_t ns, cplx* log_psi_out, cplx* eloc_out) {
     SampleSet S; S.resize(ns, psi.words);
+    S.pauli_sites = psi.pauli_sites;
     S.conf.upload(confs_host, ns * psi.words);
     psi.log_psi(S, false);
     psi.eloc(op, S);

@@ -18,6 +18,7 @@ void cholesky_solve(cplx* A, cplx* b, unsigned P, int* info_dev, DevBuf<cplx>& w
 
 struct Ensemble {
     bool is_mc = false;
+    bool paulis = false;            // MonteCarloPaulis / ExactSummationPaulis: configurations are Pauli strings (pauli_basis.cuh)
     // ExactSummation (include/ensembles/ExactSummation.hpp)
     unsigned num_sites = 0;
     // MonteCarlo (include/ensembles/MonteCarlo.hpp, source/ensembles/MonteCarlo.cu:14-42)
@@ -29,7 +30,7 @@ struct Ensemble {
     unsigned rank = (unsigned)comm_rank(), world = (unsigned)comm_world();
     DevBuf<unsigned long long> d_acc_rej;
 
-    size_t num_steps() const { return is_mc ? (size_t)num_samples : ((size_t)1 << num_sites); }
+    size_t num_steps() const { return is_mc ? (size_t)num_samples : ((size_t)1 << (paulis ? 2u * num_sites : num_sites)); }
     void shard(size_t total, size_t& begin, size_t& count) const {
         begin = total * rank / world;
         count = total * (rank + 1) / world - begin;

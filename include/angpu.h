@@ -123,6 +123,15 @@ int angpu_es_create(unsigned num_sites, angpu_ensemble_t* out);
  * states of source/RNGStates.cu:13-19) */
 int angpu_mc_create(unsigned long long num_samples, unsigned num_sweeps, unsigned num_thermalization_sweeps,
                     unsigned num_markov_chains, uint64_t seed, angpu_ensemble_t* out);
+/* ExactSummationPaulis(num_sites, gpu) / MonteCarloPaulis(...) (include/ensembles/ExactSummation.hpp:124-126,
+ * include/ensembles/MonteCarlo.hpp:265-283; bindings pyANNonGPU/main.cpp.template:369-377, 400-405): the Pauli-string
+ * (density-matrix) basis.  Configurations are Pauli strings (4^num_sites of them); the wavefunction is a PsiDeep with
+ * N = 3 num_sites input units (include/quantum_state/PsiDeep.hpp:282-308); operators act by Pauli multiplication
+ * (include/basis/PauliString.hpp:257-277).  Configurations cross the boundary as "units" masks: bit 3 s + t set iff site s
+ * carries Pauli type t + 1 (X, Y, Z) -- PauliString::network_unit_at (include/basis/PauliString.hpp:84-90). */
+int angpu_es_paulis_create(unsigned num_sites, angpu_ensemble_t* out);
+int angpu_mc_paulis_create(unsigned long long num_samples, unsigned num_sweeps, unsigned num_thermalization_sweeps,
+                           unsigned num_markov_chains, uint64_t seed, angpu_ensemble_t* out);
 int angpu_ensemble_copy(angpu_ensemble_t ens, angpu_ensemble_t* out);
 int angpu_ensemble_destroy(angpu_ensemble_t ens);
 int angpu_ensemble_num_steps(angpu_ensemble_t ens, unsigned long long* out);          /* get_num_steps() (global) */

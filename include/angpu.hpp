@@ -79,6 +79,13 @@ public:
 struct ExactSummationSpins : Ensemble {
     explicit ExactSummationSpins(unsigned num_sites) { ANGPU_CXX(angpu_es_create(num_sites, &h_)); }
 };
+struct ExactSummationPaulis : Ensemble {
+    explicit ExactSummationPaulis(unsigned num_sites) { ANGPU_CXX(angpu_es_paulis_create(num_sites, &h_)); }
+};
+struct MonteCarloPaulis : Ensemble {
+    MonteCarloPaulis(unsigned long long num_samples, unsigned num_sweeps, unsigned num_thermalization_sweeps, unsigned num_markov_chains,
+                     uint64_t seed = 0xA11CEull) { ANGPU_CXX(angpu_mc_paulis_create(num_samples, num_sweeps, num_thermalization_sweeps, num_markov_chains, seed, &h_)); }
+};
 struct MonteCarloSpins : Ensemble {
     MonteCarloSpins(unsigned long long num_samples, unsigned num_sweeps, unsigned num_thermalization_sweeps, unsigned num_markov_chains,
                     uint64_t seed = 0xA11CEull) { ANGPU_CXX(angpu_mc_create(num_samples, num_sweeps, num_thermalization_sweeps, num_markov_chains, seed, &h_)); }

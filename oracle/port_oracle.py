@@ -178,7 +178,7 @@ class Psi:
 
     @property
     def words(self):
-        return words_for(self.num_sites)
+        return words_for(getattr(self, "N", self.num_sites))      # N = 3 num_sites for a PsiDeep on the Pauli-string basis
 
     @property
     def num_params(self):

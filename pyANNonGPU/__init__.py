@@ -9,7 +9,7 @@ from annongpu_b200 import (                                   # noqa: F401
 )
 from annongpu_b200.api import (                               # noqa: F401
     PsiRBM, PsiDeep, PsiCNN, PsiClassicalFP_1, PsiClassicalFP_2, PsiClassicalANN_1, PsiClassicalANN_2, PsiFullyPolarized,
-    Operator, Spins, MonteCarloSpins, ExactSummationSpins, ExpectationValue, TDVP, HilbertSpaceDistance, KullbackLeibler,
+    Operator, Spins, MonteCarloSpins, ExactSummationSpins, MonteCarloPaulis, ExactSummationPaulis, ExpectationValue, TDVP, HilbertSpaceDistance, KullbackLeibler,
     log_psi_s, psi_O_k, psi_O_k_vector, log_psi, psi_vector, log_psi_vector, apply_operator, activation_function,
     setDevice, start_profiling, stop_profiling,
 )
