@@ -228,12 +228,40 @@ static void launch_eloc_rbm(const RbmDev& d, const Operator& op, SampleSet& S) {
     }
     ANGPU_CHECK_LAUNCH(); count_launch();
 }
+// the tile kernel (k_eloc_rbm_tile): M <= 256, <= 2 flips per group; the tile size makes the tiles fill the resident blocks in whole
+// rounds (ET_BLOCKS_PER_SM blocks per SM): the smallest number of rounds R with ceil(ns / (slots R)) <= 16 samples per tile
+template<int K>
+static bool launch_eloc_rbm_tile(const RbmDev& d, const Operator& op, SampleSet& S) {
+    const size_t slots = (size_t)ctx().num_sms * ET_BLOCKS_PER_SM;
+    unsigned st = 0;
+    for(size_t R = 1; R <= 64 && !st; R++) { const size_t t = (S.ns + slots * R - 1) / (slots * R); if(t <= 16) st = (unsigned)std::max<size_t>(t, 1); }
+    if(!st) st = 16;
+    const size_t smem = eloc_tile_smem(32u * K, st, d.words);
+    if(smem > (size_t)ctx().smem_optin / ET_BLOCKS_PER_SM) return false;
+    set_smem(k_eloc_rbm_tile<K>, smem);
+    const unsigned grid = (unsigned)std::min<size_t>((S.ns + st - 1) / st, slots * 8);
+    k_eloc_rbm_tile<K><<<grid, ET_WARPS * 32, smem, stream()>>>(d, op.dev, S.conf.p, S.angles.p, S.ns, st, S.eloc.p);
+    ANGPU_CHECK_LAUNCH(); count_launch();
+    return true;
+}
 void PsiRBM::eloc(const Operator& op, SampleSet& S) {
     require_operator_fits(op, N, words);
     if(S.ns == 0) return;
     const size_t budget = std::min<size_t>(ctx().smem_optin, 200 * 1024);
     if(op.dev.max_flips > (unsigned)RBM_ELOC_MAXF || rbm_eloc_slice_bytes(M, op.dev.num_groups, RBM_ELOC_WARPS) > budget) { generic_eloc(dev(), op, S); return; }
     ensure_angles(S);
+    {
+        // M <= 256, <= 2 flips per group, enough samples to fill the GPU: W rows in registers, a tile of samples per block
+        static const bool tile_on = [] { const char* e = getenv("ANGPU_ELOC_TILE"); return !(e && atoi(e) == 0); }();
+        if(tile_on && M <= 256u && op.dev.max_flips <= 2u && op.dev.num_groups >= 1u && S.ns >= (size_t)ctx().num_sms * 8) {
+            const RbmDev d = dev();
+            bool done = false;
+            if(M <= 64u) done = launch_eloc_rbm_tile<2>(d, op, S);
+            else if(M <= 128u) done = launch_eloc_rbm_tile<4>(d, op, S);
+            else done = launch_eloc_rbm_tile<8>(d, op, S);
+            if(done) return;
+        }
+    }
     // warps per sample: as few as keep >= 4 blocks (32 warps) per SM resident, but at least 2 (finer scheduling units);
     // ANGPU_ELOC_WPS overrides (A/B timing)
     const char* env = getenv("ANGPU_ELOC_WPS");

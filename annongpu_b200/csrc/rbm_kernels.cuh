@@ -628,6 +628,120 @@ k_eloc_rbm(const RbmDev psi, const OpDev op, const uint64_t* __restrict__ confs,
     }
 }
 
+// E_loc for PsiRBM, M <= 256 and <= 2 flips per group: the W ROWS OF A FLIP GROUP LIVE IN REGISTERS and are applied to a TILE of
+// samples whose angles sit in shared memory.  k_eloc_rbm streams the rows of every active group of every sample through L1 (C2:
+// 32 groups x 8 KB per sample, 2.1 GB per call, L1 throughput 85 %: the bound); here a warp owns a flip group, reads its rows once
+// (lane l holds the hidden units l + 32 k) and walks the samples of the tile -- 8 KB of W per (group, tile) instead of per
+// (group, sample), the angles (4 KB per sample and group) being the only per-pair traffic, from shared memory.
+//   block = 8 warps, tile = st <= 32 samples (lane t keeps sample t's configuration, coefficient and partial E_loc);
+//   warp w takes the groups g = w, w + 8, ...; per group: coefficients of all samples (lane-parallel), then for every ACTIVE sample
+//   sum_j lc0(theta_tj + d0 W_aj + d1 W_bj) over the warp; the exponentials of a group are evaluated together, one lane per sample.
+// The tile size is chosen by the host so that the tiles fill the resident blocks in whole rounds (launch_eloc_rbm_tile).
+constexpr int ET_WARPS = 8, ET_MAXS = 32, ET_BLOCKS_PER_SM = 2;   // two rows of K complex per lane: <= 128 registers
+__host__ __device__ inline size_t eloc_tile_smem(unsigned Mp, unsigned st, unsigned words) {
+    return (size_t)st * Mp * sizeof(cplx) + (size_t)(2 * ET_MAXS + ET_WARPS * ET_MAXS) * sizeof(cplx) + (size_t)ET_MAXS * words * sizeof(uint64_t);
+}
+template<int K>
+__global__ void __launch_bounds__(ET_WARPS * 32, ET_BLOCKS_PER_SM)
+k_eloc_rbm_tile(const RbmDev psi, const OpDev op, const uint64_t* __restrict__ confs, const cplx* __restrict__ angles,
+                size_t ns, unsigned st, cplx* __restrict__ eloc_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr unsigned Mp = 32u * K;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned M = psi.M, G = op.num_groups, words = op.words;
+    cplx* theta = reinterpret_cast<cplx*>(smem_raw);                        // [st][Mp], zero beyond M
+    cplx* base = theta + (size_t)st * Mp;                                    // [ET_MAXS]  sum_j lc0(theta_tj)
+    cplx* diag = base + ET_MAXS;                                             // [ET_MAXS]  diagonal strings
+    cplx* epart = diag + ET_MAXS;                                            // [ET_WARPS][ET_MAXS]
+    uint64_t* cs = reinterpret_cast<uint64_t*>(epart + ET_WARPS * ET_MAXS);  // [ET_MAXS][words]
+    const cplx* __restrict__ W = psi.W;
+    const size_t ntiles = (ns + st - 1) / st;
+    for(size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const size_t s0 = tile * st;
+        const unsigned cnt = (unsigned)min((size_t)st, ns - s0);
+        __syncthreads();                                                     // the previous tile is fully consumed
+        for(unsigned e = threadIdx.x; e < cnt * Mp; e += ET_WARPS * 32) {
+            const unsigned t = e / Mp, j = e % Mp;
+            theta[e] = (j < M) ? angles[(s0 + t) * M + j] : cplx(0.0, 0.0);
+        }
+        for(unsigned e = threadIdx.x; e < cnt * words; e += ET_WARPS * 32) cs[e] = confs[s0 * words + e];
+        __syncthreads();
+        for(unsigned t = warp; t < cnt; t += ET_WARPS) {                     // per-sample constants
+            cplx b(0.0, 0.0), dg(0.0, 0.0);
+            #pragma unroll
+            for(int k = 0; k < K; k++) { const cplx a = theta[t * Mp + lane + 32u * k]; b += lc0_pq(a.re, a.im); }
+            uint64_t c[MAXW]; conf_load(c, cs + t * words, words);
+            for(unsigned n = lane; n < op.num_diag; n += 32u) dg += string_sign_reg(op, n, c) * op.coef[n];
+            b = warp_sum(b); dg = warp_sum(dg);
+            if(lane == 0) { base[t] = b; diag[t] = dg; }
+        }
+        __syncthreads();
+        uint64_t cmine[MAXW] = {0ull, 0ull, 0ull, 0ull};                      // lane t: the configuration of sample t
+        if(lane < cnt) conf_load(cmine, cs + lane * words, words);
+        const cplx base_mine = (lane < cnt) ? base[lane] : cplx(0.0, 0.0);
+        cplx E_mine(0.0, 0.0);
+        for(unsigned g = warp; g < G; g += ET_WARPS) {
+            unsigned site[2] = {0u, 0u}; int nf = 0;
+            for(unsigned w = 0; w < words; w++) {
+                uint64_t m = op.flip[g * words + w];
+                while(m) { if(nf < 2) site[nf] = w * 64u + (unsigned)__ffsll((long long)m) - 1u; nf++; m &= m - 1ull; }
+            }
+            cplx w0[K], w1[K];
+            #pragma unroll
+            for(int k = 0; k < K; k++) {
+                const unsigned j = lane + 32u * k;
+                w0[k] = (j < M) ? ldg(&W[(size_t)site[0] * M + j]) : cplx(0.0, 0.0);
+                w1[k] = (j < M && nf > 1) ? ldg(&W[(size_t)site[1] * M + j]) : cplx(0.0, 0.0);
+            }
+            cplx C(0.0, 0.0);
+            if(lane < cnt) C = strings_coefficient_reg(op, op.group_begin[g], op.group_begin[g + 1u], cmine);
+            // the two spins of every sample at the group's sites, as +-2 factors: bit 0 / 1 of `sb`
+            const unsigned sb = (conf_spin(cmine, site[0]) > 0.0 ? 1u : 0u) | ((nf > 1 && conf_spin(cmine, site[1]) > 0.0) ? 2u : 0u);
+            unsigned active = __ballot_sync(FULL, C.re != 0.0 || C.im != 0.0);
+            cplx mine(0.0, 0.0);
+            // two active samples per pass: their warp reductions (5 dependent shuffle rounds each) overlap
+            auto trial = [&](unsigned t) -> cplx {
+                const unsigned sbt = __shfl_sync(FULL, sb, t);
+                const double d0 = (sbt & 1u) ? -2.0 : 2.0, d1 = (nf > 1) ? ((sbt & 2u) ? -2.0 : 2.0) : 0.0;       // s' - s
+                const cplx* __restrict__ th = theta + t * Mp + lane;
+                cplx acc(0.0, 0.0);
+                #pragma unroll
+                for(int k = 0; k < K; k++) {
+                    const cplx a = th[32u * k];
+                    const double x = fma(d1, w1[k].re, fma(d0, w0[k].re, a.re)), y = fma(d1, w1[k].im, fma(d0, w0[k].im, a.im));
+                    acc += lc0_pq(x, y);
+                }
+                return acc;
+            };
+            while(active) {
+                const unsigned t0 = (unsigned)__ffs((int)active) - 1u;
+                active &= active - 1u;
+                const bool two = active != 0u;                                   // warp-uniform
+                const unsigned t1 = two ? (unsigned)__ffs((int)active) - 1u : t0;
+                if(two) active &= active - 1u;
+                cplx a0 = trial(t0), a1(0.0, 0.0);
+                if(two) a1 = trial(t1);
+                #pragma unroll
+                for(int o = 16; o > 0; o >>= 1) {
+                    a0.re += __shfl_xor_sync(FULL, a0.re, o); a0.im += __shfl_xor_sync(FULL, a0.im, o);
+                    a1.re += __shfl_xor_sync(FULL, a1.re, o); a1.im += __shfl_xor_sync(FULL, a1.im, o);
+                }
+                if(lane == t0) mine = a0;
+                if(two && lane == t1) mine = a1;
+            }
+            if(C.re != 0.0 || C.im != 0.0) E_mine += C * cexp(psi.fw * (mine - base_mine));
+        }
+        epart[warp * ET_MAXS + lane] = E_mine;
+        __syncthreads();
+        if(threadIdx.x < cnt) {
+            cplx E = diag[threadIdx.x];
+            #pragma unroll
+            for(int w = 0; w < ET_WARPS; w++) E += epart[w * ET_MAXS + threadIdx.x];
+            eloc_out[s0 + threadIdx.x] = E;
+        }
+    }
+}
+
 // T[s][j] = final_weight * th0(theta_sj)
 __global__ void k_rbm_T(const RbmDev psi, const cplx* __restrict__ angles, size_t total, cplx* __restrict__ T) {
     for(size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)

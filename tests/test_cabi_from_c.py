@@ -41,7 +41,7 @@ def test_two_ranks_from_plain_c(tmp_path):
         pytest.skip("needs 2 GPUs")
     r = subprocess.run([build_two_ranks(tmp_path)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert r.stdout.startswith("E2 ")
+    assert any(line.startswith("E2 ") for line in r.stdout.splitlines()), r.stdout      # NCCL may print its version banner first
 
 
 def build_cxx(tmp_path):

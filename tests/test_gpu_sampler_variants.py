@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from annongpu_b200 import factories as F
-from helpers import make_psi, rel_err
+from helpers import make_op, make_psi, rel_err
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -69,3 +69,21 @@ def test_fp32_screened_sampler_reproduces_the_fp64_chains(gpu):
             assert ex0 == 0 and 0 <= ex1 <= 0.02 * sum(acc1), (name, ex1)
             lp0, lp1 = np.array(re0) + 1j * np.array(im0), np.array(re1) + 1j * np.array(im1)
             assert np.abs(lp0 - lp1).max() <= 1e-11, name
+
+
+@pytest.mark.parametrize("N,M,model", [(64, 256, "heisenberg"), (40, 100, "heisenberg"), (24, 40, "tfim"), (64, 256, "tfim")])
+def test_tile_local_energy_kernel_matches_the_oracle(gpu, port, N, M, model):
+    """k_eloc_rbm_tile (W rows of a flip group in registers, a tile of samples per block) is taken for M <= 256, <= 2 flips per group
+    and >= 1184 samples: E_loc per configuration against the port, on random configurations (ragged last tile included)."""
+    spec = F.rbm_spec(N, M, noise=0.03, final_weight=1.3, seed=21)
+    H = F.heisenberg(N, F.ring_bonds(N)) if model == "heisenberg" else F.tfim(N, F.ring_bonds(N), J=1.0, h=0.7)
+    psi_g, psi_p, op_g, op_p = make_psi(gpu, spec), make_psi(port, spec), make_op(gpu, H), make_op(port, H)
+    rng = np.random.default_rng(8)
+    ns = 1184 + 777
+    confs = rng.integers(0, 1 << min(N, 62), size=ns, dtype=np.uint64).reshape(ns, 1)
+    if N > 62:
+        confs ^= rng.integers(0, 2, size=(ns, 1), dtype=np.uint64) << np.uint64(63)
+    lp_g, el_g = gpu.local_energies(psi_g, op_g, confs)
+    lp_p, el_p, _ = port.eval_samples(psi_p, op_p, confs)
+    np.testing.assert_allclose(lp_g, lp_p, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(el_g, el_p, rtol=1e-10, atol=1e-10)
