@@ -317,9 +317,10 @@ def run_ours(args):
     kernel = "k_mc_rbm<8,1,true>" if M <= 512 else f"k_mc_rbm_block<{(M + 255) // 256},true>"
     roofline = {"kernel": kernel, "bound": "fp64", "achieved": flops / t_sample / 1e12, "peak": fp64_peak,
                 "unit": "TFLOP/s", "frac": flops / t_sample / 1e12 / fp64_peak,
-                # the sampler's compulsory DRAM traffic is its outputs only (W and the angle cache stay on chip); the ncu
-                # --set full capture of the 8192-chain launch reads 0.33 MB (outputs stay in the 126 MB L2)
-                "traffic": 0.328e6 if (cfg == "C2" and chains_local == 8192) else None,
+                # dram__bytes_read + dram__bytes_write of the 8192-chain launch in the ncu --set full capture of this build
+                # (profiles/r02_ncu_sampler_C2.json): 33.9 MB read -- theta_0 left in HBM by the angle GEMM -- and 0.05 MB written
+                # (the 34 MB of outputs stay in the 126 MB L2); W and the angle cache stay on chip
+                "traffic": 33.95e6 if (cfg == "C2" and chains_local == 8192) else None,
                 "algorithmic_flops": flops,
                 "peak_source": "measured in this run (angpu_measure_fp64_tflops: independent DFMA streams; MEASURED_PEAKS.json holds no "
                                "fp64 figure)",
