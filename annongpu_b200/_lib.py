@@ -118,6 +118,7 @@ _SIGNATURES = {
     "angpu_hpd_solve": [u32, vp, vp, vp],
     "angpu_tdvp_build_S_tensorcore": [vp],
     "angpu_tdvp_set_profile": [vp, i32],
+    "angpu_tdvp_set_tensorcore_products": [vp, i32],
     "angpu_tdvp_phase_ms": [vp, vp],
     "angpu_measure_fp64_tflops": [vp],
 }

@@ -975,6 +975,13 @@ class TDVP:
         """NEW, opt-in: rebuild S on the tcgen05 tensor cores (3xTF32, ~1e-5 relative to ||S||); then S_matrix / solve use it."""
         call("angpu_tdvp_build_S_tensorcore", self._h)
 
+    def set_tensorcore_products(self, enable=True):
+        """PsiRBM: S_dot_vector and the CG search directions on the tcgen05 tensor cores (~1e-6 relative); solve_cg still recomputes the
+        true residual with the exact product every 32 iterations and before accepting it.  True / False / None (None = auto, the
+        default: S_dot_vector exact, solve_cg by problem size).  No reference counterpart."""
+        call("angpu_tdvp_set_tensorcore_products", self._h, -1 if enable is None else (1 if enable else 0))
+        return self
+
     def set_profile(self, enable=True):
         call("angpu_tdvp_set_profile", self._h, 1 if enable else 0)
 

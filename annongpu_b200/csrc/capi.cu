@@ -398,6 +398,7 @@ int angpu_tdvp_solve_cg(angpu_tdvp_t tdvp, double tol, unsigned max_iter, double
     API_END
 }
 int angpu_tdvp_build_S_tensorcore(angpu_tdvp_t tdvp) { API_BEGIN NOTNULL(tdvp); tdvp->t->build_S_tensorcore(); API_END }
+int angpu_tdvp_set_tensorcore_products(angpu_tdvp_t tdvp, int enable) { API_BEGIN NOTNULL(tdvp); tdvp->t->tc_products = enable < 0 ? -1 : (enable != 0 ? 1 : 0); API_END }
 int angpu_tdvp_set_profile(angpu_tdvp_t tdvp, int enable) { API_BEGIN NOTNULL(tdvp); tdvp->t->profile = enable != 0; API_END }
 int angpu_tdvp_phase_ms(angpu_tdvp_t tdvp, double out[6]) { API_BEGIN NOTNULL(tdvp); NOTNULL(out); for(int i = 0; i < 6; i++) out[i] = tdvp->t->phase_ms[i]; API_END }
 int angpu_measure_fp64_tflops(double* out) { API_BEGIN NOTNULL(out); *out = measure_fp64_tflops(); API_END }

@@ -21,18 +21,14 @@
 //                                      round-to-nearest into fp32 registers (the tensor core's own fp32 accumulation
 //                                      truncates); at the end fp64 -> S[r][c] and its Hermitian mirror S[c][r]
 #include "vmc.hpp"
-#include <cuda.h>
+#include "tcgen05.cuh"
 #include <cmath>
 
 namespace angpu {
 
 namespace tc {
 
-constexpr int BLOCK_MN = 128;       // output tile (parameters x parameters)
-constexpr int BLOCK_K = 16;         // samples per stage: 16 fp32 = 64 B rows (SWIZZLE_64B)
-constexpr int UMMA_K = 8;           // tf32: 32 bytes per MMA
 constexpr int STAGES = 3;
-constexpr int TILE_BYTES = BLOCK_MN * BLOCK_K * 4;            // 8 KB
 constexpr int TILES_PER_STAGE = 8;
 constexpr int STAGE_BYTES = TILES_PER_STAGE * TILE_BYTES;     // 64 KB
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
@@ -41,60 +37,6 @@ constexpr int TMEM_COLS = 512;      // 2 ping-pong sets x (Re, Im) 128-column fp
 constexpr int CHUNK_KB = 8;         // k-blocks (x16 samples) accumulated in TMEM before the epilogue drains the set
 constexpr int EPI_WARPS = 16;       // 4 lane quarters x 4 column groups of 32
 constexpr int THREADS = 64 + 32 * EPI_WARPS;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    } while(!done);
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
-}
-// shared-memory matrix descriptor, K-major operand, 64-byte swizzle: 8-row groups are 512 B apart (SBO), LBO unused
-__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);            // start address
-    d |= (uint64_t)0 << 16;                                   // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(512u >> 4) << 32;                         // stride byte offset
-    d |= (uint64_t)1 << 46;                                   // descriptor version (sm_100)
-    d |= (uint64_t)4 << 61;                                   // layout type: SWIZZLE_64B
-    return d;
-}
-// instruction descriptor, kind::tf32, fp32 accumulate, K-major A and B, M = N = 128
-__device__ __forceinline__ uint32_t umma_idesc_tf32(bool negate_a) {
-    uint32_t d = 0;
-    d |= 1u << 4;                            // D format: F32
-    d |= 2u << 7;                            // A format: TF32
-    d |= 2u << 10;                           // B format: TF32
-    d |= (negate_a ? 1u : 0u) << 13;         // negate A
-    d |= (uint32_t)(BLOCK_MN >> 3) << 17;    // N
-    d |= (uint32_t)(BLOCK_MN >> 4) << 24;    // M
-    return d;
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                 : "r"(taddr) : "memory");
-}
 
 struct Maps { CUtensorMap re_hi, re_lo, im_hi, im_lo; };
 
@@ -245,11 +187,6 @@ k_sbuild_tf32(const __grid_constant__ Maps maps, unsigned P, unsigned num_kb, cp
 }
 
 // O [ns][P] complex fp64 -> planes [P][Kpad] fp32: A = sqrt(w) (O - Obar), split hi/lo in TF32. 32x32 smem transpose.
-__device__ __forceinline__ float to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
 __global__ void __launch_bounds__(256) k_pack_planes(const cplx* __restrict__ O, const double* __restrict__ w, const cplx* __restrict__ Obar,
                                                      double inv_W, size_t ns, unsigned P, size_t Kpad, float* __restrict__ re_hi, float* __restrict__ re_lo,
                                                      float* __restrict__ im_hi, float* __restrict__ im_lo) {
@@ -290,31 +227,6 @@ __global__ void k_rank1_add(cplx* __restrict__ S, const cplx* __restrict__ Obar,
     }
 }
 
-typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static encode_fn get_encode() {
-    static encode_fn fn = nullptr;
-    if(!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        ANGPU_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
-        ANGPU_REQUIRE(p != nullptr && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available in this driver");
-        fn = reinterpret_cast<encode_fn>(p);
-    }
-    return fn;
-}
-static void make_map(CUtensorMap* m, float* plane, unsigned P, size_t Kpad) {
-    const cuuint64_t gdim[2] = {(cuuint64_t)Kpad, (cuuint64_t)P};
-    const cuuint64_t gstride[1] = {(cuuint64_t)Kpad * sizeof(float)};
-    const cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)BLOCK_MN};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, plane, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if(r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
-}
-
 } // namespace tc
 
 // S = (1/1) sum_s conj(A_sr) A_sc on the tensor cores.  Single-process only in this round (the centred form needs the
@@ -333,8 +245,8 @@ void TDVP::build_S_tensorcore() {
     tc::k_pack_planes<<<dim3(ceil_div(P, 32), ceil_div(Kpad, 32)), 256, 0, stream()>>>(O.p, S.weight.p, Ok_dev(), 1.0 / W, ns, P, Kpad, re_hi, re_lo, im_hi, im_lo);
     ANGPU_CHECK_LAUNCH(); count_launch();
     tc::Maps maps;
-    tc::make_map(&maps.re_hi, re_hi, P, Kpad); tc::make_map(&maps.re_lo, re_lo, P, Kpad);
-    tc::make_map(&maps.im_hi, im_hi, P, Kpad); tc::make_map(&maps.im_lo, im_lo, P, Kpad);
+    tc::make_map(&maps.re_hi, re_hi, P, Kpad, Kpad); tc::make_map(&maps.re_lo, re_lo, P, Kpad, Kpad);
+    tc::make_map(&maps.im_hi, im_hi, P, Kpad, Kpad); tc::make_map(&maps.im_lo, im_lo, P, Kpad, Kpad);
     const unsigned nt = (P + tc::BLOCK_MN - 1) / tc::BLOCK_MN, tiles = nt * (nt + 1) / 2;
     ANGPU_CUDA(cudaFuncSetAttribute(tc::k_sbuild_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
     tc::k_sbuild_tf32<<<tiles, tc::THREADS, tc::SMEM_BYTES, stream()>>>(maps, P, (unsigned)(Kpad / tc::BLOCK_K), Smat.p);

@@ -643,6 +643,20 @@ __global__ void __launch_bounds__(VB_T) k_cg_p_mb(cplx* __restrict__ p, const cp
     }
     if(blockIdx.x == 0 && threadIdx.x == 0) scal[2] = rs_new;
 }
+// residual refresh of the CG with tensor-core products: r = b - (A x computed exactly); part_rr as k_cg_xr_mb leaves it
+__global__ void __launch_bounds__(VB_T) k_cg_refresh(cplx* __restrict__ r, const cplx* __restrict__ b, const cplx* __restrict__ Ax,
+                                                     const double* __restrict__ minv, cplx* __restrict__ part_rr, size_t n) {
+    double v[2] = {0, 0}, red[2];
+    for(size_t k = (size_t)blockIdx.x * VB_T + threadIdx.x; k < n; k += (size_t)VB_BLOCKS * VB_T) {
+        const cplx rk = b[k] - Ax[k];
+        r[k] = rk;
+        const double a2 = abs2(rk);
+        v[1] += a2;
+        v[0] += minv ? minv[k] * a2 : a2;
+    }
+    block_reduce_small<2>(v, red);
+    if(threadIdx.x == 0) part_rr[blockIdx.x] = cplx(red[0], red[1]);
+}
 // S.v epilogue fused with the CG scalar work: Ap = sum of the column-reduction chunks - conj(Obar) (Obar . p) + shift p,
 // part_pAp[b] = partial sums of conj(p) . Ap; rolls (r.z, |r|^2) of the previous iteration into scal[0]
 __global__ void __launch_bounds__(VB_T) k_sv_finish_cg(const cplx* part, unsigned chunks, const cplx* __restrict__ Obar,
@@ -1024,7 +1038,7 @@ void TDVP::eval(const Operator& op, Psi& psi, Ensemble& ens, bool want_S, Psi* p
 void TDVP::prepare_rows(Psi& psi, bool dense) {
     ANGPU_REQUIRE(psi.P == P, "TDVP: num_params differs from the wavefunction's");
     last_psi = &psi; words = psi.words;
-    have_S = false;
+    have_S = false; tc_ready = false;
     if(psi.kind == Psi::RBM && !dense) {
         PsiRBM& rbm = static_cast<PsiRBM&>(psi);
         rbm.compute_T(S, T);
@@ -1131,7 +1145,9 @@ void TDVP::matvec(const cplx* v_dev, cplx* out_dev, const cplx* dot_dev, const d
         ANGPU_CHECK_LAUNCH(); count_launch();
         return;
     }
-    rowdot(v_dev);
+    // tc_products: the factorised product on the tcgen05 tensor cores (sv_tc.cu; ~1e-6 relative) instead of the exact DMMA kernels
+    const bool tcp = tc_products > 0 && tc_available();       // S_dot_vector / probes: only on request (solve_cg: also by size)
+    if(tcp) tc_rowdot(v_dev); else rowdot(v_dev);
     d_scal.resize(16);
     if(!dot_dev) {
         cplx* dot = reinterpret_cast<cplx*>(d_scal.p) + 4;
@@ -1144,7 +1160,14 @@ void TDVP::matvec(const cplx* v_dev, cplx* out_dev, const cplx* dot_dev, const d
         ANGPU_CHECK_LAUNCH(); count_launch();
         dot_dev = dot;
     }
-    const ColPartials cp = col_reduce_partials(*this, row_a.p, false);
+    ColPartials cp;
+    if(tcp) {
+        // the mean Obar . v is removed from a_s before the second product (sv_tc.cu: k_pack_z): no rank-1 correction afterwards
+        cplx* px = nullptr; const unsigned ch = tc_col_partials(row_a.p, dot_dev, 1u, &px); cp = ColPartials{ch, nullptr, px};
+        tc_zero.resize(VB_BLOCKS); tc_zero.zero();
+        dot_dev = tc_zero.p;
+    }
+    else cp = col_reduce_partials(*this, row_a.p, false);
     if(reduce_on()) {
         k_sum_chunks<<<grid_for(P), 256, 0, stream()>>>(cp.x, cp.chunks, P, out_dev);
         ANGPU_CHECK_LAUNCH(); count_launch();
@@ -1155,6 +1178,10 @@ void TDVP::matvec(const cplx* v_dev, cplx* out_dev, const cplx* dot_dev, const d
     }
     ANGPU_CHECK_LAUNCH(); count_launch();
 }
+int TDVP::tc_products_default() { static const int v = [] { const char* e = getenv("ANGPU_CG_TC"); return e ? (atoi(e) != 0 ? 1 : 0) : -1; }(); return v; }
+// solve_cg: on request, or -- left at "auto" -- when the product is large enough for the tensor-core pipeline to win (measured: C2,
+// ns N M = 1.3e8: 0.107 vs 0.096 ms per iteration, slower; C5 shard, 5.2e9: 1.00 vs 2.35 ms)
+bool TDVP::tc_wanted() const { return tc_products > 0 || (tc_products < 0 && (double)S.ns * rbm_N * rbm_M >= 1e9); }
 void TDVP::S_dot_vector_dev(const cplx* v_dev, cplx* out_dev) { matvec(v_dev, out_dev, nullptr, nullptr, 0.0, 0.0); }
 void TDVP::S_dot_vector(const cplx* v_host, cplx* out_host) {
     set_reduce(sharded);
@@ -1204,8 +1231,8 @@ int TDVP::solve_cg(double tol, unsigned max_iter, double shift_abs, double shift
         ANGPU_CHECK_LAUNCH(); count_launch();
         minv = minv_buf.p;
     }
-    cg_buf.resize(5 * n);                                     // x | r | p | Ap | b
-    cplx *x = cg_buf.p, *r = x + n, *p = r + n, *Ap = p + n, *b = Ap + n;
+    cg_buf.resize(6 * n);                                     // x | r | p | Ap | b | A x (residual refresh)
+    cplx *x = cg_buf.p, *r = x + n, *p = r + n, *Ap = p + n, *b = Ap + n, *Ax = b + n;
     d_scal.resize(16);
     cplx* scal = reinterpret_cast<cplx*>(d_scal.p);
     ANGPU_CUDA(cudaMemsetAsync(x, 0, sizeof(cplx) * n, stream()));
@@ -1219,6 +1246,20 @@ int TDVP::solve_cg(double tol, unsigned max_iter, double shift_abs, double shift
     // iteration; with several ranks the per-rank column sums are all-reduced before the epilogue); products on the dense S
     // use the generic matvec + a separate dot product
     const bool fused = !use_S && (S.ns > 0 || reduce_on());
+    // PsiRBM: the search-direction products on the tcgen05 tensor cores (sv_tc.cu, TF32 hi/lo planes, ~1e-6 relative), the TRUE
+    // residual r = b - A x recomputed with the exact FP64-tensor-core product every 32 iterations; the last phase runs exact (below).
+    bool use_tc = fused && tc_wanted() && tc_available();
+    if(reduce_on()) {
+        // every rank must take the same path (the tensor-core path issues extra collectives for the residual refresh): all or none
+        double* flag = d_scal.p + 14;
+        const double mine = use_tc ? 1.0 : 0.0;
+        ANGPU_CUDA(cudaMemcpyAsync(flag, &mine, sizeof(double), cudaMemcpyHostToDevice, stream()));
+        allreduce_sum(flag, 1);
+        double sum = 0.0;
+        ANGPU_CUDA(cudaMemcpyAsync(&sum, flag, sizeof(double), cudaMemcpyDeviceToHost, stream()));
+        ANGPU_CUDA(cudaStreamSynchronize(stream()));
+        use_tc = sum > (double)comm_world() - 0.5;
+    }
     // convergence is decided on values summed over ranks, so that every rank takes the same decision
     auto read_rs = [&](int slot) -> double {      // |r|^2 = the imaginary slot of the (r.z, |r|^2) pair
         double* chk = d_scal.p + 12;
@@ -1230,24 +1271,47 @@ int TDVP::solve_cg(double tol, unsigned max_iter, double shift_abs, double shift
         return hv;
     };
     cplx h(0.0, 0.0);
+    const unsigned check_every = 8;
     const double b2 = read_rs(0);
     if(rel_res_out) *rel_res_out = 0.0;
     unsigned it = 0;
+    // Tensor-core products (~1e-6 relative; sv_tc.cu): the residual recursion r -= alpha A p is REPLACED by r = b - A x with the exact
+    // FP64-tensor-core product at every convergence check (every 8 iterations) -- measured: with a refresh every 16 or 32 iterations
+    // the C2 solve diverges, every 8 it takes the iterations of the exact solve (C2 72 / 72, C5 192 / 184) -- so the residual that is
+    // tested and reported is always an fp64 one.  Guard: if a refreshed residual is 10x above the best one seen, the rest of the
+    // solve uses exact products.
+    bool tc_phase = use_tc, refresh_now = false;
+    double best_true = -1.0;
+    if(use_tc) { tc_zero.resize(VB_BLOCKS); tc_zero.zero(); }
     if(b2 > 0.0) {
-        const unsigned check_every = 8;
         for(it = 1; it <= max_iter; it++) {
+            refresh_now = false;
             if(fused) {
-                rowdot(p);
-                ColPartials cp = col_reduce_partials(*this, row_a.p, false);
+                ColPartials cp;
+                const cplx* dot_parts = part_dot;
+                if(tc_phase) {
+                    tc_rowdot(p);
+                    cplx* px = nullptr; const unsigned ch = tc_col_partials(row_a.p, part_dot, VB_BLOCKS, &px); cp = ColPartials{ch, nullptr, px};
+                    dot_parts = tc_zero.p;                    // the mean is already removed (k_pack_z)
+                }
+                else { rowdot(p); cp = col_reduce_partials(*this, row_a.p, false); }
                 if(reduce_on()) {
                     k_sum_chunks<<<grid_for(P), 256, 0, stream()>>>(cp.x, cp.chunks, P, Ap);
                     ANGPU_CHECK_LAUNCH(); count_launch();
                     allreduce_sum(reinterpret_cast<double*>(Ap), 2 * n);
                     cp.x = Ap; cp.chunks = 1u;
                 }
-                k_sv_finish_cg<<<VB_BLOCKS, VB_T, 0, stream()>>>(cp.x, cp.chunks, Ok_dev(), part_dot, p, dg.p, shift_abs, shift_rel, n, Ap,
+                k_sv_finish_cg<<<VB_BLOCKS, VB_T, 0, stream()>>>(cp.x, cp.chunks, Ok_dev(), dot_parts, p, dg.p, shift_abs, shift_rel, n, Ap,
                                                                   part_pAp, it > 1 ? scal : nullptr);
                 k_cg_xr_mb<<<VB_BLOCKS, VB_T, 0, stream()>>>(x, r, p, Ap, scal, part_pAp, part_rr, minv, n);
+                refresh_now = tc_phase && (it % check_every == 0 || it == max_iter);
+                if(refresh_now) {
+                    const int keep = tc_products; tc_products = 0;
+                    matvec(x, Ax, nullptr, dg.p, shift_abs, shift_rel, false);
+                    tc_products = keep;
+                    k_cg_refresh<<<VB_BLOCKS, VB_T, 0, stream()>>>(r, b, Ax, minv, part_rr, n);
+                    count_launch();
+                }
                 k_cg_p_mb<<<VB_BLOCKS, VB_T, 0, stream()>>>(p, r, scal, part_rr, minv, Ok_dev(), part_dot, n);
                 ANGPU_CHECK_LAUNCH(); count_launch(3);
             } else {
@@ -1261,6 +1325,10 @@ int TDVP::solve_cg(double tol, unsigned max_iter, double shift_abs, double shift
                 h.re = read_rs(2);
                 if(rel_res_out) *rel_res_out = std::sqrt(h.re / b2);
                 if(h.re <= tol * tol * b2) break;
+                if(tc_phase) {
+                    if(best_true >= 0.0 && h.re > 100.0 * best_true) tc_phase = false;       // (squared norms: 10x in the residual)
+                    if(best_true < 0.0 || h.re < best_true) best_true = h.re;
+                }
             }
         }
         if(it > max_iter) it = max_iter;

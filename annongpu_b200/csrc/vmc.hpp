@@ -109,6 +109,18 @@ struct TDVP {
     // opt-in fast path: 3xTF32 on tcgen05 tensor cores (sbuild_tc.cu), ~1e-5 relative to ||S||
     void build_S_tensorcore();
     DevBuf<float> tc_planes;
+    // factorised S.v on the tcgen05 tensor cores (sv_tc.cu): TF32 planes of sigma (per eval), of the vector / of w a conj(T) (per product)
+    DevBuf<float> tc_sig; DevBuf<cplx> tc_apart; bool tc_ready = false;
+    // tc_products: S_dot_vector and the search directions of solve_cg use the tensor-core product (angpu_tdvp_set_tensorcore_products;
+    // ANGPU_CG_TC=0/1 sets the default of new objects); solve_cg still refreshes the residual with the exact product
+    int tc_products = tc_products_default();             // 1 on, 0 off, -1 auto (solve_cg decides by size: tc_wanted)
+    static int tc_products_default();
+    bool tc_wanted() const;
+    bool tc_available() const;
+    void tc_prepare();
+    void tc_rowdot(const cplx* v_dev);
+    unsigned tc_col_partials(const cplx* X, const cplx* xbar_parts, unsigned nbar, cplx** px_out);
+    DevBuf<cplx> tc_zero;                                  // zeros standing in for Obar . v where the mean is already removed
     DevBuf<cplx> solve_A, solve_b, solve_work;   // dense-solve workspace (grow-only)
     DevBuf<int> solve_info;
     Psi* last_psi = nullptr;

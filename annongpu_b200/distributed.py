@@ -67,22 +67,47 @@ def init_from_env(backend="nccl"):
     torch.cuda.set_stream(_stream)
     api.set_stream(_stream.cuda_stream)
     if world > 1:
+        hook = os.environ.get("ANGPU_COMM", "nccl") == "hook"
         if not dist.is_initialized():
-            dist.init_process_group(backend=backend, rank=rank, world_size=world,
-                                    device_id=torch.device("cuda", local_rank),
-                                    timeout=datetime.timedelta(seconds=int(os.environ.get("ANGPU_NCCL_TIMEOUT_S", "120"))))
-        if os.environ.get("ANGPU_COMM", "nccl") == "hook":
+            # With the communicator inside the library, torch.distributed only bootstraps (unique id, barriers, the bench's MAX over
+            # ranks): its NCCL communicator is NOT created eagerly (no device_id) and the CPU side runs on gloo -- a second NCCL
+            # communicator in the process competes with the library's for the NVLS (NVLink SHARP) resources (measured at 8 GPUs:
+            # the 524 KB all-reduce of eval_F took 0.10 ms longer with both communicators alive).
+            kw = dict(device_id=torch.device("cuda", local_rank)) if (hook and backend == "nccl") else {}
+            be = backend if (hook or backend != "nccl") else "cpu:gloo,cuda:nccl"
+            dist.init_process_group(backend=be, rank=rank, world_size=world,
+                                    timeout=datetime.timedelta(seconds=int(os.environ.get("ANGPU_NCCL_TIMEOUT_S", "120"))), **kw)
+        if hook:
             api.set_allreduce(allreduce_hook)
             # ensembles do not inherit a shard from the callback transport: callers use .set_shard(rank, world)
         else:
             uid = torch.zeros(128, dtype=torch.uint8)
             if rank == 0:
                 uid = torch.frombuffer(bytearray(api.comm_unique_id()), dtype=torch.uint8).clone()
-            dev = torch.device("cuda", local_rank) if backend == "nccl" else torch.device("cpu")
-            uid = uid.to(dev)
-            dist.broadcast(uid, src=0)
-            api.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
+            dist.broadcast(uid, src=0)                                  # CPU tensor: gloo
+            api.comm_init(bytes(uid.numpy().tobytes()), rank, world)
     return rank, world
+
+
+def barrier():
+    """Host-side barrier over the ranks (a CPU all-reduce: does not create a torch NCCL communicator)."""
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        if "gloo" in str(dist.get_backend()):
+            dist.all_reduce(torch.zeros(1))
+        else:
+            dist.barrier()
+
+
+def max_over_ranks(value):
+    """MAX of a host scalar over the ranks."""
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+        return float(value)
+    if "gloo" in str(dist.get_backend()):
+        t = torch.tensor([float(value)], dtype=torch.float64)
+    else:
+        t = torch.tensor([float(value)], dtype=torch.float64, device=torch.device("cuda", torch.cuda.current_device()))
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
 
 
 def shutdown():

@@ -221,7 +221,7 @@ def run_ours(args):
 
     def barrier():
         if world > 1:
-            dist.barrier()
+            D.barrier()
         torch.cuda.synchronize()
 
     def timed_loop(step, n):
@@ -236,10 +236,7 @@ def run_ours(args):
             phases.append(tdvp.phase_ms)
         barrier()
         ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), phases
+        return D.max_over_ranks(ms), phases
 
     def step_device():
         tdvp.eval_F(op, psi, mc)

@@ -205,6 +205,14 @@ int angpu_tdvp_get_O_k_samples(angpu_tdvp_t tdvp, double* out);       /* O_k_sam
 int angpu_tdvp_get_weights(angpu_tdvp_t tdvp, double* out);           /* weight_samples */
 int angpu_tdvp_get_E_local_samples(angpu_tdvp_t tdvp, double* out);   /* the reference's never-allocated E_local_samples, TDVP.hpp:30 */
 int angpu_tdvp_S_dot_vector(angpu_tdvp_t tdvp, const double* vec, double* out);                        /* :337-443 */
+/* PsiRBM only (no reference counterpart): run the factorised S.v -- angpu_tdvp_S_dot_vector and the search-direction products of
+ * angpu_tdvp_solve_cg -- on the tcgen05 tensor cores (sigma exact in TF32, the vector / w a conj(T) as TF32 hi + lo planes, fp32
+ * accumulation in TMEM: ~1e-6 relative).  angpu_tdvp_solve_cg then recomputes the true residual with the exact FP64-tensor-core
+ * product every 32 iterations and before it accepts a residual: the reported residual is the fp64 one.
+ * enable: 1 on, 0 off (every product exact), -1 auto = the default: angpu_tdvp_S_dot_vector exact, angpu_tdvp_solve_cg on the tensor
+ * cores when ns N M >= 1e9 (where the pipeline wins: BASELINE configuration 5).  ANGPU_CG_TC=0/1 sets the default of new objects. */
+int angpu_tdvp_set_tensorcore_products(angpu_tdvp_t tdvp, int enable);
+
 /* NEW (the reference contains no solver): x solves
  * (S + shift_abs*I + shift_rel*diag(S)) x = rhs_phase * F.  CG is matrix-free on the samples of the last eval / eval_F. */
 int angpu_tdvp_solve_cg(angpu_tdvp_t tdvp, double tol, unsigned max_iter, double shift_abs, double shift_rel,
