@@ -37,7 +37,7 @@ struct SvMaps { CUtensorMap a, re_hi, re_lo, im_hi, im_lo; };
 // MODE 1: ROWDOT     rows = samples (ns), cols = hidden units (M), out = a_part[blockIdx.y][s] = sum_j T[s][j] (re + i im)
 template<int MODE>
 __global__ void __launch_bounds__(SV_THREADS, 1)
-k_sv_tf32(const __grid_constant__ SvMaps maps, unsigned rows, unsigned cols, unsigned num_kb, unsigned kb_per_split,
+k_sv_tf32(const __grid_constant__ SvMaps maps, unsigned rows, unsigned cols, unsigned num_kb, unsigned kb_per_split, unsigned tiles_per_cta,
           const cplx* __restrict__ T, cplx* __restrict__ out, size_t out_stride) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -47,8 +47,16 @@ k_sv_tf32(const __grid_constant__ SvMaps maps, unsigned rows, unsigned cols, uns
                    tmem_slot = bar_tempty + 16u;
     cplx* red = reinterpret_cast<cplx*>(smem_raw + ((tiles - raw) + SV_STAGES * SV_STAGE_BYTES + 256));     // [4][128] (ROWDOT)
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const int row0 = (int)(blockIdx.x * BLOCK_MN), col0 = (int)(blockIdx.y * BLOCK_MN);
+    // COLREDUCE: one column tile (blockIdx.y), the K range [kb0, kb1) of this k-split (blockIdx.z).
+    // ROWDOT:    the whole K range, `tiles_per_cta` consecutive column tiles starting at blockIdx.y * tiles_per_cta: the accumulator
+    //            sets ping-pong over (tile, drain chunk) units, so the epilogue of one tile overlaps the MMAs of the next.
+    const int row0 = (int)(blockIdx.x * BLOCK_MN);
+    const unsigned nct = (cols + BLOCK_MN - 1) / BLOCK_MN;
+    const unsigned tile0 = (MODE == 1) ? blockIdx.y * tiles_per_cta : blockIdx.y;
+    const unsigned ntile = (MODE == 1) ? (tile0 < nct ? min(tiles_per_cta, nct - tile0) : 0u) : 1u;
     const unsigned kb0 = blockIdx.z * kb_per_split, kb1 = min(num_kb, kb0 + kb_per_split), nkb = kb1 > kb0 ? kb1 - kb0 : 0u;
+    const unsigned upt = (nkb + SV_CHUNK_KB - 1) / SV_CHUNK_KB;            // drain units per tile
+    const unsigned total_it = ntile * nkb;
 
     if(threadIdx.x == 0) {
         for(int s = 0; s < SV_STAGES; s++) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, 1); }
@@ -68,12 +76,12 @@ k_sv_tf32(const __grid_constant__ SvMaps maps, unsigned rows, unsigned cols, uns
     if(warp == 0) {
         if(lane == 0) {
             const CUtensorMap* mb[4] = {&maps.re_hi, &maps.re_lo, &maps.im_hi, &maps.im_lo};
-            for(unsigned it = 0; it < nkb; it++) {
+            for(unsigned it = 0; it < total_it; it++) {
                 const unsigned s = it % SV_STAGES, ph = (it / SV_STAGES) & 1u;
                 mbar_wait(bar_empty + 8u * s, ph ^ 1u);
                 mbar_arrive_expect_tx(bar_full + 8u * s, (uint32_t)SV_STAGE_BYTES);
                 const uint32_t base = tiles + s * SV_STAGE_BYTES;
-                const int k0 = (int)((kb0 + it) * BLOCK_K);
+                const int k0 = (int)((kb0 + it % nkb) * BLOCK_K), col0 = (int)((tile0 + it / nkb) * BLOCK_MN);
                 tma_load_2d(base, &maps.a, k0, row0, bar_full + 8u * s);
                 #pragma unroll
                 for(int q = 0; q < 4; q++) tma_load_2d(base + (uint32_t)(1 + q) * TILE_BYTES, mb[q], k0, col0, bar_full + 8u * s);
@@ -82,12 +90,12 @@ k_sv_tf32(const __grid_constant__ SvMaps maps, unsigned rows, unsigned cols, uns
     } else if(warp == 1) {
         if(lane == 0) {
             const uint32_t idesc = umma_idesc_tf32(false);
-            for(unsigned it = 0; it < nkb; it++) {
+            for(unsigned it = 0; it < total_it; it++) {
                 const unsigned s = it % SV_STAGES, ph = (it / SV_STAGES) & 1u;
-                const unsigned chunk = it / SV_CHUNK_KB, set = chunk & 1u, in_chunk = it % SV_CHUNK_KB;
+                const unsigned kb = it % nkb, unit = (it / nkb) * upt + kb / SV_CHUNK_KB, set = unit & 1u, in_chunk = kb % SV_CHUNK_KB;
                 const uint32_t acc_re = tmem_base + set * 2u * BLOCK_MN, acc_im = acc_re + (uint32_t)BLOCK_MN;
                 if(in_chunk == 0) {
-                    mbar_wait(bar_tempty + 8u * set, ((chunk >> 1) & 1u) ^ 1u);
+                    mbar_wait(bar_tempty + 8u * set, ((unit >> 1) & 1u) ^ 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
                 mbar_wait(bar_full + 8u * s, ph);
@@ -106,57 +114,59 @@ k_sv_tf32(const __grid_constant__ SvMaps maps, unsigned rows, unsigned cols, uns
                     umma_tf32(acc_im, d[0], d[4], idesc, 1u);
                 }
                 umma_commit(bar_empty + 8u * s);
-                if(in_chunk == SV_CHUNK_KB - 1 || it == nkb - 1) umma_commit(bar_tfull + 8u * set);
+                if(in_chunk == SV_CHUNK_KB - 1 || kb == nkb - 1) umma_commit(bar_tfull + 8u * set);
             }
         }
     } else {
         const unsigned quarter = warp & 3u;                 // TMEM lane quarter this warp may access
         const unsigned part = (warp - 2u) >> 2;             // 32-column group
-        float accR[32], accI[32];
-        #pragma unroll
-        for(int j = 0; j < 32; j++) { accR[j] = 0.0f; accI[j] = 0.0f; }
-        const unsigned num_chunks = (nkb + SV_CHUNK_KB - 1) / SV_CHUNK_KB;
-        for(unsigned chunk = 0; chunk < num_chunks; chunk++) {
-            const unsigned set = chunk & 1u;
-            mbar_wait(bar_tfull + 8u * set, (chunk >> 1) & 1u);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t tre = tmem_base + ((quarter * 32u) << 16) + set * 2u * BLOCK_MN + part * 32u;
-            #pragma unroll
-            for(int c16 = 0; c16 < 2; c16++) {
-                uint32_t v[16];
-                tmem_ld16(tre + (uint32_t)(c16 * 16), v);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                #pragma unroll
-                for(int j = 0; j < 16; j++) accR[c16 * 16 + j] += __uint_as_float(v[j]);
-                tmem_ld16(tre + (uint32_t)BLOCK_MN + (uint32_t)(c16 * 16), v);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                #pragma unroll
-                for(int j = 0; j < 16; j++) accI[c16 * 16 + j] += __uint_as_float(v[j]);
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if(lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_tempty + 8u * set) : "memory");
-        }
         const unsigned r = (unsigned)row0 + quarter * 32u + lane;
-        if(MODE == 0) {
-            if(r < rows) {
-                cplx* o = out + (size_t)blockIdx.z * out_stride + (size_t)r * cols;
+        cplx t(0.0, 0.0);                                   // ROWDOT: this row's sum over the column tiles of the CTA
+        for(unsigned tile = 0; tile < ntile; tile++) {
+            float accR[32], accI[32];
+            #pragma unroll
+            for(int j = 0; j < 32; j++) { accR[j] = 0.0f; accI[j] = 0.0f; }
+            for(unsigned chunk = 0; chunk < upt; chunk++) {
+                const unsigned unit = tile * upt + chunk, set = unit & 1u;
+                mbar_wait(bar_tfull + 8u * set, (unit >> 1) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tre = tmem_base + ((quarter * 32u) << 16) + set * 2u * BLOCK_MN + part * 32u;
                 #pragma unroll
-                for(int j = 0; j < 32; j++) {
-                    const unsigned c = (unsigned)col0 + part * 32u + (unsigned)j;
-                    if(c < cols) o[c] = cplx((double)accR[j], (double)accI[j]);
+                for(int c16 = 0; c16 < 2; c16++) {
+                    uint32_t v[16];
+                    tmem_ld16(tre + (uint32_t)(c16 * 16), v);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    #pragma unroll
+                    for(int j = 0; j < 16; j++) accR[c16 * 16 + j] += __uint_as_float(v[j]);
+                    tmem_ld16(tre + (uint32_t)BLOCK_MN + (uint32_t)(c16 * 16), v);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    #pragma unroll
+                    for(int j = 0; j < 16; j++) accI[c16 * 16 + j] += __uint_as_float(v[j]);
                 }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if(lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_tempty + 8u * set) : "memory");
             }
-        } else {
-            cplx t(0.0, 0.0);
-            if(r < rows) {
+            const unsigned col0 = (tile0 + tile) * BLOCK_MN;
+            if(MODE == 0) {
+                if(r < rows) {
+                    cplx* o = out + (size_t)blockIdx.z * out_stride + (size_t)r * cols;
+                    #pragma unroll
+                    for(int j = 0; j < 32; j++) {
+                        const unsigned c = col0 + part * 32u + (unsigned)j;
+                        if(c < cols) o[c] = cplx((double)accR[j], (double)accI[j]);
+                    }
+                }
+            } else if(r < rows) {
                 const cplx* __restrict__ Tr = T + (size_t)r * cols;
                 #pragma unroll
                 for(int j = 0; j < 32; j++) {
-                    const unsigned c = (unsigned)col0 + part * 32u + (unsigned)j;
+                    const unsigned c = col0 + part * 32u + (unsigned)j;
                     if(c < cols) cfma(t, Tr[c], cplx((double)accR[j], (double)accI[j]));
                 }
             }
+        }
+        if(MODE == 1) {
             red[part * BLOCK_MN + quarter * 32u + lane] = t;
             asm volatile("bar.sync 1, %0;" ::"r"(32 * SV_EPI_WARPS) : "memory");        // the 16 epilogue warps
             if(part == 0 && r < rows) {
@@ -286,14 +296,24 @@ void TDVP::tc_rowdot(const cplx* v_dev) {
     tc_planes.resize(std::max(tc_planes.n, (size_t)4 * M * std::max(K1, K2)));
     float* p0 = tc_planes.p; float* p1 = p0 + (size_t)M * K2; float* p2 = p1 + (size_t)M * K2; float* p3 = p2 + (size_t)M * K2;
     tc::k_pack_v<<<dim3(ceil_div(M, 32), ceil_div(K2, 32)), 256, 0, stream()>>>(v_dev, N, M, K2, p0, p1, p2, p3);
-    tc::SvMaps maps;
-    tc::make_map(&maps.a, sig2, ns, K2, K2);
-    tc::make_map(&maps.re_hi, p0, M, K2, K2); tc::make_map(&maps.re_lo, p1, M, K2, K2);
-    tc::make_map(&maps.im_hi, p2, M, K2, K2); tc::make_map(&maps.im_lo, p3, M, K2, K2);
-    const unsigned ncb = ceil_div(M, tc::BLOCK_MN), num_kb = (unsigned)(K2 / tc::BLOCK_K);
+    // tensor maps are cached per (buffers, shape): the buffers are grow-only, so a CG solve encodes them once
+    static thread_local struct { const void* a = nullptr; const void* b = nullptr; size_t ns = 0, K = 0; unsigned M = 0; tc::SvMaps maps; } cache;
+    if(cache.a != sig2 || cache.b != p0 || cache.ns != ns || cache.K != K2 || cache.M != M) {
+        tc::make_map(&cache.maps.a, sig2, ns, K2, K2);
+        tc::make_map(&cache.maps.re_hi, p0, M, K2, K2); tc::make_map(&cache.maps.re_lo, p1, M, K2, K2);
+        tc::make_map(&cache.maps.im_hi, p2, M, K2, K2); tc::make_map(&cache.maps.im_lo, p3, M, K2, K2);
+        cache.a = sig2; cache.b = p0; cache.ns = ns; cache.K = K2; cache.M = M;
+    }
+    const tc::SvMaps& maps = cache.maps;
+    const unsigned nct = ceil_div(M, tc::BLOCK_MN), nst = ceil_div(ns, tc::BLOCK_MN), num_kb = (unsigned)(K2 / tc::BLOCK_K);
+    // column tiles per CTA: as many as keep ~2 CTAs per SM (the tiles of a CTA pipeline through the two accumulator sets)
+    unsigned groups = std::max(1u, std::min(nct, ((unsigned)ctx().num_sms * 2u + nst - 1u) / nst));
+    const unsigned tpc = (nct + groups - 1u) / groups;
+    groups = (nct + tpc - 1u) / tpc;
+    const unsigned ncb = groups;
     tc_apart.resize((size_t)ncb * ns);
     row_a.resize(std::max<size_t>(1, ns));
-    tc::k_sv_tf32<1><<<dim3(ceil_div(ns, tc::BLOCK_MN), ncb, 1), tc::SV_THREADS, tc::SV_SMEM, stream()>>>(maps, (unsigned)ns, M, num_kb, num_kb, T.p, tc_apart.p, ns);
+    tc::k_sv_tf32<1><<<dim3(nst, groups, 1), tc::SV_THREADS, tc::SV_SMEM, stream()>>>(maps, (unsigned)ns, M, num_kb, num_kb, tpc, T.p, tc_apart.p, ns);
     tc::k_sum_a_parts<<<(unsigned)std::min<size_t>((ns + 255) / 256, (size_t)ctx().num_sms * 8), 256, 0, stream()>>>(tc_apart.p, ncb, ns, row_a.p);
     ANGPU_CHECK_LAUNCH(); count_launch(3);
 }
@@ -308,10 +328,14 @@ unsigned TDVP::tc_col_partials(const cplx* X, const cplx* xbar_parts, unsigned n
     tc_planes.resize(std::max(tc_planes.n, (size_t)4 * M * std::max(K1, pad16(N))));
     float* p0 = tc_planes.p; float* p1 = p0 + (size_t)M * K1; float* p2 = p1 + (size_t)M * K1; float* p3 = p2 + (size_t)M * K1;
     tc::k_pack_z<<<dim3(ceil_div(M, 32), ceil_div(K1, 32)), 256, 0, stream()>>>(T.p, S.weight.p, X, xbar_parts, nbar, ns, M, K1, p0, p1, p2, p3);
-    tc::SvMaps maps;
-    tc::make_map(&maps.a, sig1, N, K1, K1);
-    tc::make_map(&maps.re_hi, p0, M, K1, K1); tc::make_map(&maps.re_lo, p1, M, K1, K1);
-    tc::make_map(&maps.im_hi, p2, M, K1, K1); tc::make_map(&maps.im_lo, p3, M, K1, K1);
+    static thread_local struct { const void* a = nullptr; const void* b = nullptr; size_t K = 0; unsigned N = 0, M = 0; tc::SvMaps maps; } cache;
+    if(cache.a != sig1 || cache.b != p0 || cache.K != K1 || cache.N != N || cache.M != M) {
+        tc::make_map(&cache.maps.a, sig1, N, K1, K1);
+        tc::make_map(&cache.maps.re_hi, p0, M, K1, K1); tc::make_map(&cache.maps.re_lo, p1, M, K1, K1);
+        tc::make_map(&cache.maps.im_hi, p2, M, K1, K1); tc::make_map(&cache.maps.im_lo, p3, M, K1, K1);
+        cache.a = sig1; cache.b = p0; cache.K = K1; cache.N = N; cache.M = M;
+    }
+    const tc::SvMaps& maps = cache.maps;
     const unsigned nrt = ceil_div(N, tc::BLOCK_MN), nct = ceil_div(M, tc::BLOCK_MN), num_kb = (unsigned)(K1 / tc::BLOCK_K);
     // k-splits: enough CTAs for ~2 per SM, whole drain chunks (8 k-blocks = 128 samples) per split, <= 64 partials
     unsigned splits = std::max(1u, std::min(64u, ((unsigned)ctx().num_sms * 2u + nrt * nct - 1u) / (nrt * nct)));
@@ -320,7 +344,7 @@ unsigned TDVP::tc_col_partials(const cplx* X, const cplx* xbar_parts, unsigned n
     splits = (num_kb + kb_per - 1u) / kb_per;
     chunk_buf.resize(std::max(chunk_buf.n, (size_t)2 * splits * P));
     cplx* px = chunk_buf.p + (size_t)splits * P;
-    tc::k_sv_tf32<0><<<dim3(nrt, nct, splits), tc::SV_THREADS, tc::SV_SMEM, stream()>>>(maps, N, M, num_kb, kb_per, nullptr, px, (size_t)P);
+    tc::k_sv_tf32<0><<<dim3(nrt, nct, splits), tc::SV_THREADS, tc::SV_SMEM, stream()>>>(maps, N, M, num_kb, kb_per, 1u, nullptr, px, (size_t)P);
     ANGPU_CHECK_LAUNCH(); count_launch(2);
     *px_out = px;
     return splits;
