@@ -116,6 +116,9 @@ void Psi::add_params_dev(const cplx* x_dev, cplx alpha) {
 
 // ---------------------------------------------------------------------------------------- PsiRBM
 
+// ANGPU_MC_SCREEN=1 selects the fp32-screened sampler (rbm_sampler.cuh); its fp32 weight table is only kept when it is on
+static bool rbm_screen_on() { static const bool v = [] { const char* e = getenv("ANGPU_MC_SCREEN"); return e && atoi(e) != 0; }(); return v; }
+
 // W += alpha x on every device copy of the weights: W itself, the row-padded copy and the fp32 copy of the screened sampler
 __global__ void k_rbm_add_params(cplx* __restrict__ W, cplx* __restrict__ Wpad, float4* __restrict__ Wf, const cplx* __restrict__ x,
                                  cplx alpha, unsigned N, unsigned M, unsigned Mpad, unsigned KK) {
@@ -151,8 +154,12 @@ PsiRBM::PsiRBM(unsigned N_, unsigned M_, const cplx* W, cplx fw_, cplx lp_) {
     hW.assign(W, W + (size_t)N * M);
     upload();
 }
-void PsiRBM::upload() {
-    dW.upload(hW);
+void PsiRBM::upload(const cplx* src) {
+    // the host -> device copy is issued first and straight from the caller's buffer (pinned in the end-to-end path); the host
+    // mirror is refreshed while it is in flight
+    dW.resize((size_t)N * M);
+    ANGPU_CUDA(cudaMemcpyAsync(dW.p, src ? src : hW.data(), sizeof(cplx) * (size_t)N * M, cudaMemcpyHostToDevice, stream()));
+    if(src) { hW.assign(src, src + (size_t)N * M); host_stale = false; }
     // rows padded to a multiple of 32*K (warp sampler) / 256 (block sampler) complex for the register-resident samplers
     // (rbm_kernels.cuh); when M already is such a multiple (C2: 256) the samplers read W itself
     Mpad = 0;
@@ -163,8 +170,8 @@ void PsiRBM::upload() {
             for(unsigned i = 0; i < N; i++) std::memcpy(&wp[(size_t)i * Mpad], &hW[(size_t)i * M], sizeof(cplx) * M);
             dWpad.upload(wp);
         }
-        if(M <= 512u) {
-            // fp32 copy for the screened sampler (rbm_sampler.cuh): float4 (Re W_pj0, Re W_pj1, Im W_pj0, Im W_pj1) at
+        if(M <= 512u && rbm_screen_on()) {
+            // fp32 copy for the (opt-in) screened sampler (rbm_sampler.cuh): float4 (Re W_pj0, Re W_pj1, Im W_pj0, Im W_pj1) at
             // [(p KK + kk) 32 + lane], j0 = 64 kk + 2 lane, zeros beyond M
             const unsigned KK = rbm_sampler_KK(M);
             std::vector<float4> wf((size_t)N * KK * 32u);
@@ -178,6 +185,7 @@ void PsiRBM::upload() {
             dWf.upload(wf);
         }
     }
+    ANGPU_CUDA(cudaStreamSynchronize(stream()));          // src may be short-lived
 }
 // theta = sigma W for a batch of configurations: the FP64 tensor-core GEMM (k_rbm_angles_dmma) for batches that fill the
 // m8 tiles, the warp-per-configuration kernel for probes of a few configurations; ANGPU_ANGLES=fma forces the latter
@@ -253,11 +261,11 @@ void PsiRBM::eloc(const Operator& op, SampleSet& S) {
     {
         // M <= 256, <= 2 flips per group, enough samples to fill the GPU: W rows in registers, a tile of samples per block
         static const bool tile_on = [] { const char* e = getenv("ANGPU_ELOC_TILE"); return !(e && atoi(e) == 0); }();
-        if(tile_on && M <= 256u && op.dev.max_flips <= 2u && op.dev.num_groups >= 1u && S.ns >= (size_t)ctx().num_sms * 8) {
+        // (narrow layers, M <= 64, stay on the team kernel: measured at C1, M = 32, the tile kernel costs 0.08 ms of 0.31)
+        if(tile_on && M > 64u && M <= 256u && op.dev.max_flips <= 2u && op.dev.num_groups >= 1u && S.ns >= (size_t)ctx().num_sms * 8) {
             const RbmDev d = dev();
             bool done = false;
-            if(M <= 64u) done = launch_eloc_rbm_tile<2>(d, op, S);
-            else if(M <= 128u) done = launch_eloc_rbm_tile<4>(d, op, S);
+            if(M <= 128u) done = launch_eloc_rbm_tile<4>(d, op, S);
             else done = launch_eloc_rbm_tile<8>(d, op, S);
             if(done) return;
         }
@@ -354,7 +362,7 @@ void PsiRBM::mc_sample(const McParams& mc, SampleSet& S, unsigned long long* acc
         // ANGPU_MC_SCREEN=1 selects the fp32-screened sampler (rbm_sampler.cuh): identical chains, but measured SLOWER than
         // the all-fp64 sampler on B200 (C2: 2.3 vs 1.75 ms; FP32 runs at only 2x the FP64 rate, F2F at a quarter of it, and
         // the kernel is issue-bound -- DESIGN.md 9.1), so it is opt-in
-        static const bool screen_on = [] { const char* e = getenv("ANGPU_MC_SCREEN"); return e && atoi(e) != 0; }();
+        const bool screen_on = rbm_screen_on();
         const unsigned long long steps = (unsigned long long)N * ((unsigned long long)mc.num_therm + (unsigned long long)mc.num_sweeps * mc.steps_per_chain);
         const bool screened = screen_on && fw.im == 0.0 && steps < 0xffffffffull;
         switch(rbm_sampler_KK(M)) {

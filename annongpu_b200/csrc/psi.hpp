@@ -77,13 +77,13 @@ struct PsiRBM : Psi {
 
     PsiRBM(unsigned N_, unsigned M_, const cplx* W, cplx fw_, cplx lp_);
     RbmDev dev() const { return RbmDev{N, M, words, P, lp, fw, dW.p, (float)(2.0 * fw.re)}; }
-    void upload();
+    void upload(const cplx* src = nullptr);      // src: the caller's buffer (copied to the device straight from there), else hW
     // the device copies are updated in place by add_params_dev; the host copy is refreshed lazily
     mutable bool host_stale = false;
     void sync_host() const;
     Psi* clone() const override { sync_host(); return new PsiRBM(N, M, hW.data(), fw, lp); }
     void get_params(cplx* out) const override { sync_host(); std::memcpy(out, hW.data(), sizeof(cplx) * P); }
-    void set_params(const cplx* in) override { hW.assign(in, in + P); host_stale = false; upload(); }
+    void set_params(const cplx* in) override { upload(in); }
     void add_params_dev(const cplx* x_dev, cplx alpha) override;
     void log_psi(SampleSet& S, bool es_weights) override;
     void eloc(const Operator& op, SampleSet& S) override;

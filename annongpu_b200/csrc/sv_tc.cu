@@ -274,6 +274,7 @@ bool TDVP::tc_available() const { return factorised && S.ns >= 128 && rbm_M >= 3
 // sigma planes of the samples of the last eval (once per eval: the configurations do not change during a solve)
 void TDVP::tc_prepare() {
     if(tc_ready) return;
+    (void)tc::get_encode();                       // throws when the driver lacks cuTensorMapEncodeTiled: solve_cg (auto) then stays exact
     const size_t ns = S.ns, K1 = pad16(ns), K2 = pad16(rbm_N);
     tc_sig.resize((size_t)rbm_N * K1 + ns * K2);
     float* sig1 = tc_sig.p; float* sig2 = sig1 + (size_t)rbm_N * K1;

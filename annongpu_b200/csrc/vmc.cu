@@ -1249,6 +1249,9 @@ int TDVP::solve_cg(double tol, unsigned max_iter, double shift_abs, double shift
     // PsiRBM: the search-direction products on the tcgen05 tensor cores (sv_tc.cu, TF32 hi/lo planes, ~1e-6 relative), the TRUE
     // residual r = b - A x recomputed with the exact FP64-tensor-core product every 32 iterations; the last phase runs exact (below).
     bool use_tc = fused && tc_wanted() && tc_available();
+    if(use_tc && tc_products < 0) {                       // auto mode never fails because of the fast path: fall back to exact products
+        try { tc_prepare(); } catch(const Error&) { cudaGetLastError(); use_tc = false; }
+    }
     if(reduce_on()) {
         // every rank must take the same path (the tensor-core path issues extra collectives for the residual refresh): all or none
         double* flag = d_scal.p + 14;

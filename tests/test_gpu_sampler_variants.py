@@ -71,9 +71,9 @@ def test_fp32_screened_sampler_reproduces_the_fp64_chains(gpu):
             assert np.abs(lp0 - lp1).max() <= 1e-11, name
 
 
-@pytest.mark.parametrize("N,M,model", [(64, 256, "heisenberg"), (40, 100, "heisenberg"), (24, 40, "tfim"), (64, 256, "tfim")])
+@pytest.mark.parametrize("N,M,model", [(64, 256, "heisenberg"), (40, 100, "heisenberg"), (24, 72, "tfim"), (64, 256, "tfim")])
 def test_tile_local_energy_kernel_matches_the_oracle(gpu, port, N, M, model):
-    """k_eloc_rbm_tile (W rows of a flip group in registers, a tile of samples per block) is taken for M <= 256, <= 2 flips per group
+    """k_eloc_rbm_tile (W rows of a flip group in registers, a tile of samples per block) is taken for 64 < M <= 256, <= 2 flips per group
     and >= 1184 samples: E_loc per configuration against the port, on random configurations (ragged last tile included)."""
     spec = F.rbm_spec(N, M, noise=0.03, final_weight=1.3, seed=21)
     H = F.heisenberg(N, F.ring_bonds(N)) if model == "heisenberg" else F.tfim(N, F.ring_bonds(N), J=1.0, h=0.7)
