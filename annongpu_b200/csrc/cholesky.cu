@@ -317,17 +317,36 @@ void cholesky_solve(cplx* A, cplx* b, unsigned P, int* info_dev, DevBuf<cplx>& w
     // Two-level blocking: diagonal blocks and block rows of CH_NB rows, trailing updates of a GROUP of G block rows at a time (1/G of the
     // passes over the trailing matrix, G times the work per tile of k_zherk_dmma).  Inside a group only the NEXT block row is brought
     // up to date after each block row -- the first two tile rows (128 complex rows) of the update, which k_zherk_dmma enumerates first.
-    auto herk = [&](unsigned r0, unsigned nrows, unsigned c0, unsigned tile_rows) {
+    auto herk = [&](cudaStream_t st, unsigned r0, unsigned nrows, unsigned c0, unsigned tile_rows) {
         // A[c0:, c0:] -= U[r0:r0+nrows, c0:]^dagger U[r0:r0+nrows, c0:], restricted to the first `tile_rows` tile rows (0 = all)
         const unsigned cols = P - c0, nt = (cols + 63u) / 64u;
         unsigned tiles = nt * (nt + 1u) / 2u;
         if(tile_rows && tile_rows < nt) tiles = tile_rows * nt - tile_rows * (tile_rows - 1u) / 2u;
-        k_zherk_dmma<4, true><<<dim3(tiles, 1), 512, ZD_SMEM, stream()>>>(reinterpret_cast<const double*>(A + (size_t)r0 * lda + c0), 2 * lda, nullptr,
-                                                                             (size_t)nrows, cols, (size_t)nrows, A + (size_t)c0 * lda + c0, lda, 0);
+        k_zherk_dmma<4, true><<<dim3(tiles, 1), 512, ZD_SMEM, st>>>(reinterpret_cast<const double*>(A + (size_t)r0 * lda + c0), 2 * lda, nullptr,
+                                                                      (size_t)nrows, cols, (size_t)nrows, A + (size_t)c0 * lda + c0, lda, 0);
         count_launch();
     };
     static const unsigned G = [] { const char* e = getenv("ANGPU_CHOL_GROUP"); const int g = e ? atoi(e) : CH_GROUP; return (unsigned)std::max(1, std::min(g, 16)); }();
+    // Look-ahead: the trailing update of a group is issued in two parts -- first the rows of the NEXT group (the tile-row prefix of the
+    // update), then everything below -- and the next group's chain of small kernels (diagonal factor, inverse, block row, in-group
+    // updates: single-SM latency) runs on a second, high-priority stream while the second part streams on the main one.  The chain
+    // touches only the next group's rows, the second part only the rows below them.  ANGPU_CHOL_LOOKAHEAD=0 serialises everything.
+    static const bool lookahead = [] { const char* e = getenv("ANGPU_CHOL_LOOKAHEAD"); return !(e && atoi(e) == 0); }();
+    static cudaStream_t side = nullptr;
+    static cudaEvent_t ev_part_a = nullptr, ev_chain = nullptr;
+    if(lookahead && !side) {
+        int lo = 0, hi = 0;
+        ANGPU_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        ANGPU_CUDA(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, hi));
+        ANGPU_CUDA(cudaEventCreateWithFlags(&ev_part_a, cudaEventDisableTiming));
+        ANGPU_CUDA(cudaEventCreateWithFlags(&ev_chain, cudaEventDisableTiming));
+    }
+    const cudaStream_t S0 = stream();
+    bool chain_on_side = false;
     for(unsigned K0 = 0, kb = 0; K0 < P; K0 += G * CH_NB) {
+        const cudaStream_t cs = chain_on_side ? side : S0;
+        if(chain_on_side) ANGPU_CUDA(cudaStreamWaitEvent(side, ev_part_a, 0));      // this group's rows are up to date
+        bool joined = !chain_on_side;
         for(unsigned sub = 0; sub < G; sub++, kb++) {
             const unsigned k0 = K0 + sub * CH_NB;
             if(k0 >= P) break;
@@ -336,17 +355,31 @@ void cholesky_solve(cplx* A, cplx* b, unsigned P, int* info_dev, DevBuf<cplx>& w
             cplx* Akk = A + (size_t)k0 * lda + k0;
             cplx* Tk = Tall + (size_t)kb * CH_NB * CH_NB;
             const size_t pack = (size_t)nb * (nb + 1) / 2 * sizeof(cplx);
-            k_chol_diag<<<1, 1024, pack, stream()>>>(Akk, lda, nb, (int)k0, info_dev);
-            k_tri_inv<<<1, TI_T, TI_SMEM, stream()>>>(Akk, lda, nb, Tk);
+            k_chol_diag<<<1, 1024, pack, cs>>>(Akk, lda, nb, (int)k0, info_dev);
+            k_tri_inv<<<1, TI_T, TI_SMEM, cs>>>(Akk, lda, nb, Tk);
             count_launch(2);
             if(k1 < P) {
-                k_chol_panel_gemm<<<ceil_div(P - k1, PG_C), PG_T, 0, stream()>>>(Tk, Akk + nb, lda, nb, P - k1);
+                k_chol_panel_gemm<<<ceil_div(P - k1, PG_C), PG_T, 0, cs>>>(Tk, Akk + nb, lda, nb, P - k1);
                 count_launch();
-                if(sub + 1 < G) herk(K0, k1 - K0, k1, CH_NB / 64);                   // the group's rows so far onto the next block row only
-                else herk(K0, k1 - K0, k1, 0);                                       // the whole group onto everything below
+                if(sub + 1 < G) herk(cs, K0, k1 - K0, k1, CH_NB / 64);               // the group's rows so far onto the next block row only
+                else {
+                    // the whole group onto everything below: the next group's rows first, then the rest
+                    if(!joined) { ANGPU_CUDA(cudaEventRecord(ev_chain, side)); ANGPU_CUDA(cudaStreamWaitEvent(S0, ev_chain, 0)); joined = true; }
+                    const unsigned c_mid = std::min(P, k1 + G * (unsigned)CH_NB);
+                    if(lookahead && c_mid < P) {
+                        herk(S0, K0, k1 - K0, k1, (c_mid - k1) / 64u);
+                        ANGPU_CUDA(cudaEventRecord(ev_part_a, S0));
+                        herk(S0, K0, k1 - K0, c_mid, 0);
+                        chain_on_side = true;
+                    } else {
+                        herk(S0, K0, k1 - K0, k1, 0);
+                        chain_on_side = false;
+                    }
+                }
             }
             ANGPU_CHECK_LAUNCH();
         }
+        if(!joined) { ANGPU_CUDA(cudaEventRecord(ev_chain, side)); ANGPU_CUDA(cudaStreamWaitEvent(S0, ev_chain, 0)); }   // the factor ends inside this group
     }
     // U^dagger y = b
     for(unsigned k0 = 0, kb = 0; k0 < P; k0 += CH_NB, kb++) {
