@@ -74,6 +74,8 @@ def init_from_env(backend="nccl"):
             # communicator in the process competes with the library's for the NVLS (NVLink SHARP) resources (measured at 8 GPUs:
             # the 524 KB all-reduce of eval_F took 0.10 ms longer with both communicators alive).
             kw = dict(device_id=torch.device("cuda", local_rank)) if (hook and backend == "nccl") else {}
+            if os.environ.get("MASTER_ADDR", "127.0.0.1") in ("127.0.0.1", "localhost"):
+                os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")       # single node: gloo must not depend on the hostname resolving
             be = backend if (hook or backend != "nccl") else "cpu:gloo,cuda:nccl"
             dist.init_process_group(backend=be, rank=rank, world_size=world,
                                     timeout=datetime.timedelta(seconds=int(os.environ.get("ANGPU_NCCL_TIMEOUT_S", "120"))), **kw)
