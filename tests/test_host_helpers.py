@@ -28,3 +28,25 @@ def test_shard_range_partitions_exactly():
             parts = [shard_range(total, r, world) for r in range(world)]
             assert sum(n for _, n in parts) == total
             assert all(parts[i][0] + parts[i][1] == parts[i + 1][0] for i in range(world - 1)) and parts[0][0] == 0
+
+
+def test_pauli_units_round_trip_matches_the_oracle():
+    """The boundary form of a Pauli string (units mask: bit 3 s + t <-> site s carries type t + 1) is the same in the product's host
+    helper and in the oracle port, and converts back exactly (PauliString::network_unit_at, include/basis/PauliString.hpp:84-90)."""
+    import numpy as np
+    from annongpu_b200.api import paulis_to_units, units_to_paulis
+    from oracle import port_oracle as P
+    rng = np.random.default_rng(1)
+    for ns in (1, 3, 21, 22, 40, 64, 85):
+        for _ in range(8):
+            a, b = int(rng.integers(0, 1 << min(ns, 62))), int(rng.integers(0, 1 << min(ns, 62)))
+            u = paulis_to_units(a, b, ns)
+            assert u.shape == ((3 * ns + 63) // 64,)
+            assert units_to_paulis(u, ns) == (a, b)
+            words = (ns + 63) // 64
+            pa = np.array([(a >> (64 * w)) & 0xFFFFFFFFFFFFFFFF for w in range(words)], dtype=np.uint64)
+            pb = np.array([(b >> (64 * w)) & 0xFFFFFFFFFFFFFFFF for w in range(words)], dtype=np.uint64)
+            assert np.array_equal(u, P.paulis_to_units(pa, pb, ns))
+            # at most one unit per site
+            v = sum(int(x) << (64 * w) for w, x in enumerate(u))
+            assert all(bin((v >> (3 * s)) & 7).count("1") <= 1 for s in range(ns))
