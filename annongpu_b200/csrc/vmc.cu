@@ -1254,14 +1254,16 @@ int TDVP::solve_cg(double tol, unsigned max_iter, double shift_abs, double shift
     }
     if(reduce_on()) {
         // every rank must take the same path (the tensor-core path issues extra collectives for the residual refresh): all or none
+        // (votes, ranks) summed over the ranks -- the rank count comes from the reduction itself, so this also holds for the callback
+        // transport, which does not know the world size
         double* flag = d_scal.p + 14;
-        const double mine = use_tc ? 1.0 : 0.0;
-        ANGPU_CUDA(cudaMemcpyAsync(flag, &mine, sizeof(double), cudaMemcpyHostToDevice, stream()));
-        allreduce_sum(flag, 1);
-        double sum = 0.0;
-        ANGPU_CUDA(cudaMemcpyAsync(&sum, flag, sizeof(double), cudaMemcpyDeviceToHost, stream()));
+        const double mine[2] = {use_tc ? 1.0 : 0.0, 1.0};
+        ANGPU_CUDA(cudaMemcpyAsync(flag, mine, 2 * sizeof(double), cudaMemcpyHostToDevice, stream()));
+        allreduce_sum(flag, 2);
+        double sum[2] = {0.0, 0.0};
+        ANGPU_CUDA(cudaMemcpyAsync(sum, flag, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream()));
         ANGPU_CUDA(cudaStreamSynchronize(stream()));
-        use_tc = sum > (double)comm_world() - 0.5;
+        use_tc = sum[0] > sum[1] - 0.5;
     }
     // convergence is decided on values summed over ranks, so that every rank takes the same decision
     auto read_rs = [&](int slot) -> double {      // |r|^2 = the imaginary slot of the (r.z, |r|^2) pair
