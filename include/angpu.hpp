@@ -206,6 +206,8 @@ public:
         std::vector<complex_t> out(P_); ANGPU_CXX(angpu_tdvp_S_dot_vector(h_, dptr(v.data()), dptr(out.data()))); return out;
     }
     struct CgResult { std::vector<complex_t> x; unsigned iterations; double rel_residual; };
+    // PsiRBM: CG search directions / S_dot_vector on the tcgen05 tensor cores (1 on, 0 off, -1 auto = default); the residual stays fp64
+    void set_tensorcore_products(int enable) { ANGPU_CXX(angpu_tdvp_set_tensorcore_products(h_, enable)); }
     CgResult solve_cg(double tol = 1e-6, unsigned max_iter = 1000, double shift_abs = 0.0, double shift_rel = 1e-3, complex_t rhs_phase = 1.0) {
         CgResult r{std::vector<complex_t>(P_), 0u, 0.0};
         const double ph[2] = {rhs_phase.real(), rhs_phase.imag()};
