@@ -47,6 +47,10 @@ def _worker(rank, world, port_file, out_file):
     dist.all_reduce(t, op=dist.ReduceOp.SUM)                       # the hook's job (annongpu_b200/distributed.py)
     gathered = [None] * world
     dist.all_gather_object(gathered, (c0, cn, confs))
+    # the bench's host-side helpers on the gloo side of the process group (no torch NCCL communicator is created for them)
+    from annongpu_b200 import distributed as D
+    D.barrier()
+    assert D.max_over_ranks(10.0 + rank) == 10.0 + (world - 1)
     if rank == 0:
         np.savez(out_file, packed=t.numpy().view(np.complex128), shards=np.array([(g[0], g[1]) for g in gathered]),
                  confs=np.concatenate([g[2].reshape(PER_CHAIN, g[1], -1) for g in gathered], axis=1).reshape(CHAINS * PER_CHAIN, -1))
